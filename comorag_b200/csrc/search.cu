@@ -1,0 +1,458 @@
+// K4: fused query-block x corpus-shard bf16 inner product + exact top-k + running
+// (min, max), one persistent CTA per SM.
+//
+// Replaces the reference's per-query  np.dot(E, q.T) -> min_max_normalize ->
+// np.argsort(...)[::-1]  (ComoRAG.py:937-967, embed_utils.py:153-158) for up to
+// 32 queries per pass over the shard, without ever writing the [nq, N] score
+// matrix.
+//
+// Data flow per CTA (192 threads):
+//   warp 0   TMA producer: streams the shard as 128-row x 64-col bf16 boxes
+//            (16 KB, 128-byte swizzle) through a STAGES-deep mbarrier ring; the
+//            32 x dim query block is TMA-staged once and stays in smem.
+//   warp 1   tcgen05.mma issuer: scores[128 rows, 32 queries] accumulate in
+//            TMEM (fp32) over dim/16 UMMA steps; two accumulator buffers so the
+//            next tile's MMAs overlap this tile's select.
+//   warps 2-5  select: each thread owns one corpus row of the tile (one TMEM
+//            lane), reads its 32 scores with tcgen05.ld, updates per-query
+//            min/max in registers and offers scores that beat the query's
+//            current k-th best to a small shared candidate buffer; full
+//            buffers are bitonic-sorted in registers by one warp (topk.cuh).
+// The shard is read exactly once from HBM: algorithmic bytes = n_rows*dim*2.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "topk.cuh"
+
+namespace crag {
+
+constexpr int kTileRows = 128;  // UMMA M: corpus rows per tile
+constexpr int kBlockK = 64;     // bf16 per 128-byte swizzle row
+constexpr int kNQ = 32;         // UMMA N: queries per pass
+constexpr int kStageBytes = kTileRows * kBlockK * 2;  // 16 KB
+constexpr int kQBlockBytes = kNQ * kBlockK * 2;       // 4 KB
+constexpr int kSearchThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr uint32_t kTmemCols = 64;  // 2 accumulator buffers x 32 columns
+
+template <int KLIST, int CAP, int STAGES>
+struct SearchLayout {
+  static constexpr int kKeysPerQuery = KLIST + CAP;
+  __host__ __device__ static constexpr size_t keys_bytes() { return size_t(kNQ) * kKeysPerQuery * 8; }
+  __host__ __device__ static constexpr size_t misc_bytes() {
+    return (2 * STAGES + 5) * 8    // mbarriers
+           + kNQ * 8               // thr_key
+           + kNQ * 4               // thr_f
+           + kNQ * 4               // cnt
+           + 4 * kNQ * 2 * 4       // min/max cross-warp reduction
+           + 16;                   // tmem base
+  }
+  __host__ static size_t smem_bytes(int num_kb) {
+    return 1024 + size_t(STAGES) * kStageBytes + size_t(num_kb) * kQBlockBytes + keys_bytes() + misc_bytes();
+  }
+};
+
+template <int KLIST, int CAP, int STAGES>
+__global__ void __launch_bounds__(kSearchThreads, 1)
+search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_constant__ CUtensorMap tm_q,
+                   int n_rows, int num_kb, int nq, int k, uint64_t* __restrict__ part_keys,
+                   float* __restrict__ part_minmax) {
+  using L = SearchLayout<KLIST, CAP, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint8_t* stage_base = smem;
+  uint8_t* q_base = stage_base + STAGES * kStageBytes;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(q_base + num_kb * kQBlockBytes);
+  uint64_t* bar_full = keys + kNQ * L::kKeysPerQuery;
+  uint64_t* bar_empty = bar_full + STAGES;
+  uint64_t* bar_tfull = bar_empty + STAGES;   // [2]
+  uint64_t* bar_tempty = bar_tfull + 2;       // [2]
+  uint64_t* bar_q = bar_tempty + 2;           // [1]
+  uint64_t* thr_key = bar_q + 1;              // [kNQ]
+  float* thr_f = reinterpret_cast<float*>(thr_key + kNQ);  // [kNQ]
+  int* cnt = reinterpret_cast<int*>(thr_f + kNQ);          // [kNQ]
+  float* red = reinterpret_cast<float*>(cnt + kNQ);        // [4][kNQ][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red + 4 * kNQ * 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = (n_rows + kTileRows - 1) / kTileRows;
+
+  // ------------------------------------------------------------ one-time setup
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_corpus);
+    tma_prefetch_desc(&tm_q);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bar_tfull[a], 1);
+      mbar_init(&bar_tempty[a], 4);  // one arrive per select warp
+    }
+    mbar_init(bar_q, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  // selector state: empty lists, thresholds at -inf
+  for (int i = threadIdx.x; i < kNQ * L::kKeysPerQuery; i += kSearchThreads) keys[i] = 0ull;
+  if (threadIdx.x < kNQ) {
+    thr_key[threadIdx.x] = 0ull;
+    thr_f[threadIdx.x] = -INFINITY;
+    cnt[threadIdx.x] = 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_q, num_kb * kQBlockBytes);
+      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(&tm_q, bar_q, q_base + kb * kQBlockBytes, kb * kBlockK, 0);
+      const uint64_t pol = policy_evict_first();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bar_full[stage], kStageBytes);
+          tma_load_2d_hint(&tm_corpus, &bar_full[stage], stage_base + stage * kStageBytes, kb * kBlockK,
+                           tile * kTileRows, pol);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================== MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileRows, kNQ);
+      mbar_wait(bar_q, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kNQ;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(stage_base + stage * kStageBytes);
+          const uint32_t b_addr = smem_u32(q_base + kb * kQBlockBytes);
+#pragma unroll
+          for (int ks = 0; ks < kBlockK / 16; ++ks) {
+            umma_f16(d_tmem, umma_desc_k_sw128(a_addr + ks * 32), umma_desc_k_sw128(b_addr + ks * 32), idesc,
+                     (kb | ks) != 0);
+          }
+          umma_commit(&bar_empty[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bar_tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================================================================== select
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int ew = warp - 2;    // select-warp index 0..3 (query ownership for flushes)
+    float mn[kNQ], mx[kNQ];
+#pragma unroll
+    for (int q = 0; q < kNQ; ++q) { mn[q] = INFINITY; mx[q] = -INFINITY; }
+
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&bar_tfull[acc], acc_phase);
+      tc_fence_after();
+      uint32_t r[kNQ];
+      tmem_ld_32x32b_x32(tmem_base + (uint32_t(quad * 32) << 16) + acc * kNQ, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+
+      const int row = tile * kTileRows + quad * 32 + lane;
+      uint32_t pending = 0;
+      if (row < n_rows) {
+#pragma unroll
+        for (int q = 0; q < kNQ; ++q) {
+          const float s = __uint_as_float(r[q]);
+          mn[q] = fminf(mn[q], s);
+          mx[q] = fmaxf(mx[q], s);
+          if (s >= thr_f[q]) pending |= 1u << q;
+        }
+        if (nq < kNQ) pending &= (1u << nq) - 1u;
+      }
+      while (true) {
+        bool want_flush = false;
+#pragma unroll
+        for (int q = 0; q < kNQ; ++q) {
+          if ((pending >> q) & 1u) {
+            const int slot = atomicAdd(&cnt[q], 1);
+            if (slot < CAP) {
+              keys[q * L::kKeysPerQuery + KLIST + slot] = make_key(__uint_as_float(r[q]), uint32_t(row));
+              pending &= ~(1u << q);
+            }
+            if (slot >= CAP - 1) want_flush = true;
+          }
+        }
+        if (!named_bar_or(1, kEpiThreads, want_flush || pending != 0)) break;
+        for (int q = ew; q < kNQ; q += 4) {
+          const int c = cnt[q];
+          if (c >= CAP) {
+            flush_query<KLIST, CAP>(keys + q * L::kKeysPerQuery, CAP, k, &thr_key[q], lane);
+            if (lane == 0) {
+              const uint64_t t = thr_key[q];
+              thr_f[q] = t ? key_score(t) : -INFINITY;
+              cnt[q] = 0;
+            }
+          }
+        }
+        named_bar_sync(1, kEpiThreads);
+        if (pending) {
+#pragma unroll
+          for (int q = 0; q < kNQ; ++q) {
+            if (((pending >> q) & 1u) && make_key(__uint_as_float(r[q]), uint32_t(row)) < thr_key[q])
+              pending &= ~(1u << q);
+          }
+        }
+      }
+    }
+
+    // drain candidate buffers, then publish this CTA's lists and (min, max)
+    named_bar_sync(1, kEpiThreads);
+    for (int q = ew; q < kNQ; q += 4) {
+      const int c = min(cnt[q], CAP);
+      if (c > 0) flush_query<KLIST, CAP>(keys + q * L::kKeysPerQuery, c, k, &thr_key[q], lane);
+      __syncwarp();
+      uint64_t* dst = part_keys + (size_t(blockIdx.x) * kNQ + q) * k;
+      for (int j = lane; j < k; j += 32) dst[j] = keys[q * L::kKeysPerQuery + j];
+    }
+#pragma unroll
+    for (int q = 0; q < kNQ; ++q) {
+      float a = mn[q], b = mx[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+      }
+      if (lane == q) {
+        red[(ew * kNQ + q) * 2 + 0] = a;
+        red[(ew * kNQ + q) * 2 + 1] = b;
+      }
+    }
+    named_bar_sync(1, kEpiThreads);
+    if (ew == 0) {
+      float a = red[lane * 2], b = red[lane * 2 + 1];
+#pragma unroll
+      for (int w = 1; w < 4; ++w) {
+        a = fminf(a, red[(w * kNQ + lane) * 2]);
+        b = fmaxf(b, red[(w * kNQ + lane) * 2 + 1]);
+      }
+      part_minmax[(size_t(blockIdx.x) * kNQ + lane) * 2 + 0] = a;
+      part_minmax[(size_t(blockIdx.x) * kNQ + lane) * 2 + 1] = b;
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------
+// Merge kernels: one warp per query streams candidate keys through the same
+// selector.  PAIRS=false: raw keys (local row ids) from search_topk_kernel's
+// CTAs, ids are widened and offset on output.  PAIRS=true: (score, int64 id)
+// pairs from several shards; ties resolve by candidate position.
+template <int KLIST, int CAP, bool PAIRS>
+__global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restrict__ part_keys,
+                                                         const float* __restrict__ in_scores,
+                                                         const int64_t* __restrict__ in_ids,
+                                                         const float* __restrict__ part_minmax, int parts,
+                                                         int q_stride, int nq, int k, int64_t row_offset,
+                                                         int64_t* __restrict__ out_ids,
+                                                         float* __restrict__ out_scores,
+                                                         float* __restrict__ out_minmax) {
+  constexpr int KPQ = KLIST + CAP;
+  __shared__ uint64_t s_keys[4][KPQ];
+  __shared__ uint64_t s_thr[4];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + w;
+  if (q >= nq) return;
+  uint64_t* keys = s_keys[w];
+  for (int i = lane; i < KPQ; i += 32) keys[i] = 0ull;
+  if (lane == 0) s_thr[w] = 0ull;
+  __syncwarp();
+
+  int c = 0;
+  const int total = parts * k;
+  for (int base = 0; base < total; base += 32) {
+    const int idx = base + lane;
+    uint64_t key = 0;
+    if (idx < total) {
+      const int p = idx / k, j = idx - p * k;
+      if (PAIRS) {
+        const size_t at = (size_t(p) * q_stride + q) * k + j;
+        if (in_ids[at] >= 0) key = make_key(in_scores[at], uint32_t(idx));
+      } else {
+        key = part_keys[(size_t(p) * q_stride + q) * k + j];
+      }
+    }
+    const bool take = key != 0 && key > s_thr[w];
+    const uint32_t m = __ballot_sync(0xffffffffu, take);
+    if (take) keys[KLIST + c + __popc(m & ((1u << lane) - 1u))] = key;
+    c += __popc(m);
+    __syncwarp();
+    if (c + 32 > CAP) {
+      flush_query<KLIST, CAP>(keys, c, k, &s_thr[w], lane);
+      c = 0;
+    }
+  }
+  if (c > 0) flush_query<KLIST, CAP>(keys, c, k, &s_thr[w], lane);
+  __syncwarp();
+  for (int j = lane; j < k; j += 32) {
+    const uint64_t key = keys[j];
+    float s = -INFINITY;
+    int64_t id = -1;
+    if (key) {
+      s = key_score(key);
+      id = PAIRS ? in_ids[(size_t(key_id(key) / k) * q_stride + q) * k + key_id(key) % k]
+                 : int64_t(key_id(key)) + row_offset;
+    }
+    out_scores[size_t(q) * k + j] = s;
+    out_ids[size_t(q) * k + j] = id;
+  }
+  if (out_minmax != nullptr) {
+    float a = INFINITY, b = -INFINITY;
+    if (part_minmax != nullptr) {
+      for (int p = lane; p < parts; p += 32) {
+        a = fminf(a, part_minmax[(size_t(p) * q_stride + q) * 2 + 0]);
+        b = fmaxf(b, part_minmax[(size_t(p) * q_stride + q) * 2 + 1]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if (lane == 0) {
+      out_minmax[size_t(q) * 2 + 0] = a;
+      out_minmax[size_t(q) * 2 + 1] = b;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+namespace {
+
+struct SearchPlan {
+  int grid;
+  size_t keys_bytes;    // per 32-query pass
+  size_t minmax_bytes;  // per 32-query pass
+};
+
+SearchPlan plan_search(int k) {
+  SearchPlan p;
+  p.grid = sm_count();
+  if (p.grid <= 0) p.grid = 148;
+  p.keys_bytes = ((size_t(p.grid) * kNQ * k * 8) + 255) & ~size_t(255);
+  p.minmax_bytes = ((size_t(p.grid) * kNQ * 2 * 4) + 255) & ~size_t(255);
+  return p;
+}
+
+template <int KLIST, int CAP, int STAGES>
+int launch_search(const CUtensorMap& tm_corpus, const CUtensorMap& tm_q, int n_rows, int num_kb, int nq, int k,
+                  int grid, uint64_t* part_keys, float* part_minmax, cudaStream_t stream) {
+  using L = SearchLayout<KLIST, CAP, STAGES>;
+  const size_t smem = L::smem_bytes(num_kb);
+  auto kern = search_topk_kernel<KLIST, CAP, STAGES>;
+  CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, n_rows, num_kb, nq, k, part_keys, part_minmax);
+  CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
+}
+
+}  // namespace
+}  // namespace crag
+
+using namespace crag;
+
+extern "C" size_t crag_search_workspace_bytes(int nq, int k) {
+  (void)nq;
+  if (k < 1 || k > 128) return 0;
+  const SearchPlan p = plan_search(k);
+  return p.keys_bytes + p.minmax_bytes;
+}
+
+extern "C" int crag_search_topk(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride,
+                                int64_t row_offset, const void* queries, int nq, int k, int64_t* out_ids,
+                                float* out_scores, float* out_minmax, void* workspace, size_t workspace_bytes,
+                                crag_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (nq < 1 || k < 1 || k > 128) return fail(CRAG_ERR_INVALID, "crag_search_topk: need nq >= 1 and 1 <= k <= 128 (nq=%d k=%d)", nq, k);
+  if (dim < 64 || dim > 1024 || dim % 64 != 0) return fail(CRAG_ERR_INVALID, "crag_search_topk: dim must be a multiple of 64 in [64, 1024] (dim=%d)", dim);
+  if (n_rows < 0 || n_rows >= (int64_t(1) << 31) - kTileRows) return fail(CRAG_ERR_INVALID, "crag_search_topk: n_rows out of range (%lld)", (long long)n_rows);
+  if (corpus_row_stride < dim || corpus_row_stride % 8 != 0) return fail(CRAG_ERR_INVALID, "crag_search_topk: corpus_row_stride must be >= dim and a multiple of 8");
+  if (!queries || !out_ids || !out_scores || !workspace || (n_rows > 0 && !corpus)) return fail(CRAG_ERR_INVALID, "crag_search_topk: null pointer");
+  if ((reinterpret_cast<uintptr_t>(corpus) | reinterpret_cast<uintptr_t>(queries)) & 15) return fail(CRAG_ERR_INVALID, "crag_search_topk: corpus/queries must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(CRAG_ERR_INVALID, "crag_search_topk: workspace must be 256-byte aligned");
+  const SearchPlan plan = plan_search(k);
+  if (workspace_bytes < plan.keys_bytes + plan.minmax_bytes) return fail(CRAG_ERR_WORKSPACE, "crag_search_topk: workspace %zu < %zu bytes", workspace_bytes, plan.keys_bytes + plan.minmax_bytes);
+
+  uint64_t* part_keys = static_cast<uint64_t*>(workspace);
+  float* part_minmax = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes);
+  const int num_kb = dim / kBlockK;
+  const int num_tiles = int((n_rows + kTileRows - 1) / kTileRows);
+  const int grid = num_tiles < plan.grid ? num_tiles : plan.grid;
+
+  CUtensorMap tm_corpus;
+  if (n_rows > 0) {
+    int rc = make_tmap_bf16_2d(&tm_corpus, corpus, uint64_t(n_rows), uint64_t(dim), uint64_t(corpus_row_stride) * 2, kTileRows);
+    if (rc != CRAG_OK) return rc;
+  }
+  for (int q0 = 0; q0 < nq; q0 += kNQ) {
+    const int nqc = (nq - q0) < kNQ ? (nq - q0) : kNQ;
+    if (grid > 0) {
+      CUtensorMap tm_q;
+      int rc = make_tmap_bf16_2d(&tm_q, static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2, uint64_t(nqc), uint64_t(dim), uint64_t(dim) * 2, kNQ);
+      if (rc != CRAG_OK) return rc;
+      if (k <= 64) rc = launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nqc, k, grid, part_keys, part_minmax, stream);
+      else rc = launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nqc, k, grid, part_keys, part_minmax, stream);
+      if (rc != CRAG_OK) return rc;
+    }
+    const int mgrid = (nqc + 3) / 4;
+    float* omm = out_minmax ? out_minmax + size_t(q0) * 2 : nullptr;
+    if (k <= 64)
+      merge_topk_kernel<64, 64, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nqc, k, row_offset, out_ids + size_t(q0) * k, out_scores + size_t(q0) * k, omm);
+    else
+      merge_topk_kernel<128, 128, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nqc, k, row_offset, out_ids + size_t(q0) * k, out_scores + size_t(q0) * k, omm);
+    CRAG_CUDA_OK(cudaGetLastError());
+  }
+  return CRAG_OK;
+}
+
+extern "C" int crag_merge_topk(const float* scores, const int64_t* ids, const float* minmax, int parts, int nq,
+                               int k, int64_t* out_ids, float* out_scores, float* out_minmax,
+                               crag_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (parts < 0 || nq < 1 || k < 1 || k > 128 || int64_t(parts) * k > (1 << 20)) return fail(CRAG_ERR_INVALID, "crag_merge_topk: bad sizes (parts=%d nq=%d k=%d)", parts, nq, k);
+  if (!out_ids || !out_scores || (parts > 0 && (!scores || !ids))) return fail(CRAG_ERR_INVALID, "crag_merge_topk: null pointer");
+  const int mgrid = (nq + 3) / 4;
+  if (k <= 64)
+    merge_topk_kernel<64, 64, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, minmax, parts, nq, nq, k, 0, out_ids, out_scores, out_minmax);
+  else
+    merge_topk_kernel<128, 128, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, minmax, parts, nq, nq, k, 0, out_ids, out_scores, out_minmax);
+  CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
+}

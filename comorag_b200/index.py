@@ -1,0 +1,174 @@
+"""Device-resident bf16 corpus shard + fused top-k search (host side of K4).
+
+The reference keeps its index as a host fp32 matrix rebuilt from the
+EmbeddingStore (ComoRAG.py:876-907) and scores one query at a time with
+np.dot + min_max_normalize + np.argsort (ComoRAG.py:937-967).  Here the matrix
+lives in HBM as bf16 [n_rows, dim_pad] and a whole query block is scored per
+pass by libcomorag_b200's crag_search_topk.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native
+
+MAX_DIM = 1024
+MAX_K = 128
+
+
+def _pad_dim(dim: int) -> int:
+    return (dim + 63) // 64 * 64
+
+
+class DenseIndex:
+    """One corpus shard in HBM.
+
+    ``row_offset`` is the global id of local row 0 (rank r of a row-sharded
+    index owns ids [row_offset, row_offset + n_rows)).
+    """
+
+    def __init__(self, dim: int, device: Optional[torch.device] = None, capacity: int = 0, row_offset: int = 0):
+        if dim < 1:
+            raise ValueError("dim must be positive")
+        self.dim = int(dim)
+        self.dim_pad = _pad_dim(self.dim)
+        if self.dim_pad > MAX_DIM:
+            raise ValueError(f"dim {dim} > {MAX_DIM} is not supported by the sm_100a search kernel")
+        if device is None:
+            if not torch.cuda.is_available():
+                raise _native.NativeError("DenseIndex needs a CUDA device (no CPU fallback)")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.row_offset = int(row_offset)
+        self._n = 0
+        self._buf = torch.zeros((max(int(capacity), 0), self.dim_pad), dtype=torch.bfloat16, device=self.device)
+        self._lock = threading.Lock()
+        _native.load()
+
+    # ------------------------------------------------------------------ build
+    @classmethod
+    def from_tensor(cls, rows: torch.Tensor, row_offset: int = 0) -> "DenseIndex":
+        """Adopt a device bf16 [n, dim] tensor (dim % 64 == 0) without copying."""
+        if rows.dtype != torch.bfloat16 or rows.dim() != 2 or not rows.is_cuda:
+            raise ValueError("from_tensor expects a CUDA bf16 [n, dim] tensor")
+        if rows.shape[1] % 64 != 0 or rows.stride(1) != 1 or rows.stride(0) % 8 != 0:
+            raise ValueError("from_tensor needs dim % 64 == 0 and a row stride that is a multiple of 8")
+        self = cls(rows.shape[1], device=rows.device, row_offset=row_offset)
+        self._buf = rows
+        self._n = rows.shape[0]
+        return self
+
+    @property
+    def n_rows(self) -> int:
+        return self._n
+
+    def matrix(self) -> torch.Tensor:
+        """bf16 view [n_rows, dim] of the stored rows."""
+        return self._buf[: self._n, : self.dim]
+
+    def _reserve(self, n: int) -> None:
+        if n <= self._buf.shape[0]:
+            return
+        cap = max(n, int(self._buf.shape[0] * 1.5) + 1024)
+        new = torch.zeros((cap, self.dim_pad), dtype=torch.bfloat16, device=self.device)
+        new[: self._n] = self._buf[: self._n]
+        self._buf = new
+
+    def add(self, vectors) -> None:
+        """Append rows (numpy / torch, any float dtype, [n, dim]); stored as bf16."""
+        v = torch.as_tensor(vectors)
+        if v.dim() == 1:
+            v = v[None, :]
+        if v.shape[1] != self.dim:
+            raise ValueError(f"expected [n, {self.dim}] vectors, got {tuple(v.shape)}")
+        with self._lock:
+            n0, n1 = self._n, self._n + v.shape[0]
+            self._reserve(n1)
+            self._buf[n0:n1, : self.dim] = v.to(self.device, non_blocking=True).to(torch.bfloat16)
+            self._n = n1
+
+    # ----------------------------------------------------------------- search
+    def search_device(self, queries: torch.Tensor, k: int,
+                      stream: Optional[torch.cuda.Stream] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Top-k of a device bf16 [nq, dim_pad] query block.
+
+        Returns (ids int64 [nq, k], scores fp32 [nq, k], minmax fp32 [nq, 2]),
+        all on the device, enqueued on ``stream`` (default: current stream).
+        Scores are raw inner products sorted descending (ties: ascending id);
+        missing entries (n_rows < k) have id -1 / score -inf.
+        """
+        if not (1 <= k <= MAX_K):
+            raise ValueError(f"k must be in [1, {MAX_K}]")
+        if queries.dtype != torch.bfloat16 or queries.dim() != 2 or queries.shape[1] != self.dim_pad:
+            raise ValueError(f"queries must be bf16 [nq, {self.dim_pad}]")
+        if not queries.is_contiguous():
+            queries = queries.contiguous()
+        nq = queries.shape[0]
+        lib = _native.load()
+        dev = self.device
+        with torch.cuda.device(dev):
+            st = stream if stream is not None else torch.cuda.current_stream(dev)
+            with torch.cuda.stream(st):
+                ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+                scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+                minmax = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+                ws_bytes = lib.crag_search_workspace_bytes(nq, k)
+                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+                rc = lib.crag_search_topk(
+                    self._buf.data_ptr() if self._n else 0, self._n, self.dim_pad, self._buf.stride(0) if self._buf.dim() == 2 and self._buf.shape[0] else self.dim_pad,
+                    self.row_offset, queries.data_ptr(), nq, k, ids.data_ptr(), scores.data_ptr(),
+                    minmax.data_ptr(), ws.data_ptr(), ws_bytes, st.cuda_stream)
+                _native.check(rc, "crag_search_topk")
+        return ids, scores, minmax
+
+    def prepare_queries(self, queries) -> torch.Tensor:
+        """Host/device float [nq, dim] -> device bf16 [nq, dim_pad]."""
+        q = torch.as_tensor(queries)
+        if q.dim() == 1:
+            q = q[None, :]
+        if q.shape[1] != self.dim:
+            raise ValueError(f"expected [nq, {self.dim}] queries, got {tuple(q.shape)}")
+        if not q.is_cuda:
+            q = q.pin_memory() if q.dtype in (torch.float32, torch.bfloat16, torch.float16) else q
+        q = q.to(self.device, non_blocking=True).to(torch.bfloat16)
+        if self.dim_pad != self.dim:
+            qp = torch.zeros((q.shape[0], self.dim_pad), dtype=torch.bfloat16, device=self.device)
+            qp[:, : self.dim] = q
+            q = qp
+        return q
+
+    def search(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Host-buffer entry point: numpy in, numpy out (ids, scores, minmax)."""
+        q = self.prepare_queries(queries)
+        ids, scores, minmax = self.search_device(q, k)
+        out = torch.cat([ids.to(torch.float64).view(-1), scores.to(torch.float64).view(-1),
+                         minmax.to(torch.float64).view(-1)]).cpu().numpy()
+        nq = q.shape[0]
+        return (out[: nq * k].astype(np.int64).reshape(nq, k),
+                out[nq * k: 2 * nq * k].astype(np.float32).reshape(nq, k),
+                out[2 * nq * k:].astype(np.float32).reshape(nq, 2))
+
+
+def merge_topk(scores: torch.Tensor, ids: torch.Tensor, minmax: Optional[torch.Tensor]):
+    """Merge [parts, nq, k] per-shard results into the global top-k (device)."""
+    if scores.dim() != 3 or ids.shape != scores.shape:
+        raise ValueError("scores/ids must be [parts, nq, k]")
+    parts, nq, k = scores.shape
+    lib = _native.load()
+    dev = scores.device
+    scores = scores.contiguous().to(torch.float32)
+    ids = ids.contiguous().to(torch.int64)
+    mm = minmax.contiguous().to(torch.float32) if minmax is not None else None
+    out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_mm = torch.empty((nq, 2), dtype=torch.float32, device=dev) if mm is not None else None
+    with torch.cuda.device(dev):
+        rc = lib.crag_merge_topk(scores.data_ptr(), ids.data_ptr(), _native.ptr(mm), parts, nq, k,
+                                 out_ids.data_ptr(), out_scores.data_ptr(), _native.ptr(out_mm),
+                                 torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(rc, "crag_merge_topk")
+    return out_ids, out_scores, out_mm

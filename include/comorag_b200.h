@@ -1,0 +1,108 @@
+/*
+ * libcomorag_b200 -- C ABI of the B200 (sm_100a) embedding + dense-retrieval
+ * engine that sits behind ComoRAG's embedding_model / EmbeddingStore call
+ * surfaces.
+ *
+ * The reference (EternityJune25/ComoRAG) is pure Python and has no FFI of its
+ * own; every entry point below names the reference arithmetic it replaces
+ * (file:line relative to the reference tree).  The Python host layer in
+ * comorag_b200/ binds these with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "device" is a CUDA device
+ *     pointer owned by the caller (PyTorch's allocator in the Python host);
+ *   - nothing here allocates, frees or synchronises: all work is enqueued on
+ *     the given stream; scratch space is a caller-provided workspace whose size
+ *     comes from the matching *_workspace_bytes();
+ *   - return value 0 = CRAG_OK, negative = error; crag_last_error() returns the
+ *     calling thread's message.  No C++ exception crosses the boundary;
+ *   - re-entrant: concurrent calls from different host threads on different
+ *     streams are safe (the reference calls in from up to 16 threads,
+ *     ComoRAG.py:436-441).
+ */
+#ifndef COMORAG_B200_H_
+#define COMORAG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CRAG_API __attribute__((visibility("default")))
+#else
+#define CRAG_API
+#endif
+
+#define CRAG_OK 0
+#define CRAG_ERR_INVALID (-1)   /* bad argument (shape, alignment, null) */
+#define CRAG_ERR_CUDA (-2)      /* a CUDA runtime/driver call failed */
+#define CRAG_ERR_WORKSPACE (-3) /* workspace too small */
+#define CRAG_ERR_UNSUPPORTED (-4)
+
+/* Opaque CUDA stream handle (cudaStream_t). */
+typedef void* crag_stream_t;
+
+/* Library ABI version (major*1000 + minor). */
+CRAG_API int crag_version(void);
+/* Message for the last failing call made by the calling thread ("" if none). */
+CRAG_API const char* crag_last_error(void);
+/* Number of SMs of the current device (148 on B200); <0 on error. */
+CRAG_API int crag_sm_count(void);
+
+/* ------------------------------------------------------------------ search
+ * Fused brute-force inner-product top-k over one corpus shard.
+ *
+ * Replaces, for a batch of nq queries at once, the reference's per-query
+ *     scores = np.dot(E, q.T); scores = min_max_normalize(scores);
+ *     order  = np.argsort(scores)[::-1]            (ComoRAG.py:950-967,
+ *                                                   ComoRAG.py:937-948 + :475,
+ *                                                   embed_utils.py:153-158)
+ * without materialising the [nq, n_rows] score matrix: each query gets its k
+ * best rows (raw inner products, descending; equal scores ordered by ascending
+ * row id) plus the global (min, max) over ALL n_rows scores, from which the
+ * reference's min-max-normalised score of any survivor is
+ * (s - min) / (max - min)  (misc_utils.py:141-150).
+ *
+ *   corpus      device, bf16 [n_rows, dim] row-major, row stride
+ *               corpus_row_stride elements (>= dim, multiple of 8), 16-B aligned
+ *   n_rows      rows in this shard, 0 <= n_rows < 2^31
+ *   dim         embedding width, multiple of 64, 64 <= dim <= 1024
+ *   row_offset  added to local row indices to form the ids written out
+ *               (the shard's first global row; 0 for an unsharded index)
+ *   queries     device, bf16 [nq, dim] row-major contiguous, 16-B aligned
+ *   nq          number of queries, >= 1 (processed 32 per corpus pass)
+ *   k           1 <= k <= 128
+ *   out_ids     device, int64 [nq, k]; -1 where fewer than k rows exist
+ *   out_scores  device, fp32  [nq, k]; -inf where fewer than k rows exist
+ *   out_minmax  device, fp32  [nq, 2] = (min, max) over the shard's scores;
+ *               (+inf, -inf) for an empty shard.  May be NULL.
+ *   workspace   device scratch of >= crag_search_workspace_bytes(nq, k) bytes,
+ *               256-B aligned
+ */
+CRAG_API size_t crag_search_workspace_bytes(int nq, int k);
+CRAG_API int crag_search_topk(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride, int64_t row_offset,
+                     const void* queries, int nq, int k, int64_t* out_ids, float* out_scores, float* out_minmax,
+                     void* workspace, size_t workspace_bytes, crag_stream_t stream);
+
+/* Merge `parts` per-shard results (the all-gathered output of
+ * crag_search_topk on every rank, rank-major) into the global top-k.
+ *
+ * This is the exchange step the row-sharded index adds on top of the
+ * reference; on one shard it is the identity.
+ *
+ *   scores  device fp32  [parts, nq, k]   ids  device int64 [parts, nq, k]
+ *   minmax  device fp32  [parts, nq, 2]   (may be NULL together with out_minmax)
+ * Invalid candidates are marked by id < 0.  Equal scores are ordered by
+ * (part, position), which equals ascending global id when parts own ascending
+ * contiguous row ranges.  k <= 128, parts * k <= 2^20.
+ */
+CRAG_API int crag_merge_topk(const float* scores, const int64_t* ids, const float* minmax, int parts, int nq, int k,
+                    int64_t* out_ids, float* out_scores, float* out_minmax, crag_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMORAG_B200_H_ */
