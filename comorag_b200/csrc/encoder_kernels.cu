@@ -1,0 +1,455 @@
+// Non-GEMM kernels of the encoder forward (BGEEmbedding.py:92-129 =
+// HF BertModel forward -> mean_pooling (BGEEmbedding.py:15-28) ->
+// F.normalize (:127)), operating on the UNPADDED token stream: sequences are
+// packed back to back ([T, H], T = sum of lengths, cu_seqlens[n+1]), which is
+// arithmetically identical to the reference's pad-to-longest + attention-mask
+// because padded keys get -inf logits and padded rows are dropped by the
+// masked mean.
+//
+//   embed_layernorm   word+position+token_type(0) embedding gather + LayerNorm
+//   layernorm         LayerNorm of (GEMM-out + bias + residual), fused in the
+//                     GEMM epilogue, fp32 statistics, bf16 in/out
+//   attention         varlen multi-head self-attention, flash-style online
+//                     softmax, mma.sync m16n8k16 bf16 tiles (round-1 kernel; the
+//                     GEMMs carry ~92% of the flops and run on tcgen05)
+//   pool_normalize    K3: masked mean over tokens + L2 normalise, writes fp32
+//                     [n, H] for the host API and (optionally) the bf16 row
+//                     straight into the corpus shard
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "encoder.cuh"
+
+namespace crag {
+
+// --------------------------------------------------------------- LayerNorm
+// One warp per row; each lane owns VPL 16-byte vectors (8 bf16) of the row.
+template <int VPL>
+__device__ __forceinline__ void warp_layernorm_store(float (&x)[VPL][8], int H, int lane, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps,
+                                                     __nv_bfloat16* __restrict__ orow) {
+  const int nvec = H / 8;
+  float sum = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+    if (lane + v * 32 < nvec)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += x[v][j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / float(H);
+  float var = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+    if (lane + v * 32 < nvec)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = x[v][j] - mean;
+        var += d * d;
+      }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / float(H) + eps);
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int vec = lane + v * 32;
+    if (vec < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vec * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vec * 8 + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      __nv_bfloat162 o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o[j] = __floats2bfloat162_rn((x[v][2 * j] - mean) * rstd * g[2 * j] + b[2 * j],
+                                     (x[v][2 * j + 1] - mean) * rstd * g[2 * j + 1] + b[2 * j + 1]);
+      *reinterpret_cast<uint4*>(orow + vec * 8) = *reinterpret_cast<uint4*>(o);
+    }
+  }
+}
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& raw, float (&f)[8]) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __bfloat162float(p[j].x);
+    f[2 * j + 1] = __bfloat162float(p[j].y);
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(128) embed_layernorm_kernel(const int32_t* __restrict__ token_ids,
+                                                              const int32_t* __restrict__ cu_seqlens, int n_seqs,
+                                                              int T, int H, int vocab, int max_pos, int pos_offset,
+                                                              const __nv_bfloat16* __restrict__ word_emb,
+                                                              const __nv_bfloat16* __restrict__ pos_emb,
+                                                              const __nv_bfloat16* __restrict__ type_emb,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps,
+                                                              __nv_bfloat16* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 4 + warp;
+  if (t >= T) return;
+  // position within the owning sequence: binary search cu_seqlens (n_seqs is small)
+  int lo = 0, hi = n_seqs;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(cu_seqlens + mid) <= t) lo = mid; else hi = mid;
+  }
+  int pos = t - __ldg(cu_seqlens + lo) + pos_offset;
+  pos = pos < max_pos ? pos : max_pos - 1;
+  int id = __ldg(token_ids + t);
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const int nvec = H / 8;
+  float x[VPL][8];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int vec = lane + v * 32;
+    if (vec < nvec) {
+      float a[8], b[8], c[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(word_emb + int64_t(id) * H + vec * 8)), a);
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(pos_emb + int64_t(pos) * H + vec * 8)), b);
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(type_emb + vec * 8)), c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[v][j] = a[j] + b[j] + c[j];
+    }
+  }
+  warp_layernorm_store<VPL>(x, H, lane, gamma, beta, eps, out + int64_t(t) * H);
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(128) layernorm_kernel(const __nv_bfloat16* __restrict__ in, int T, int H,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps,
+                                                        __nv_bfloat16* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 4 + warp;
+  if (t >= T) return;
+  const int nvec = H / 8;
+  float x[VPL][8];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int vec = lane + v * 32;
+    if (vec < nvec) bf16x8_to_float(*reinterpret_cast<const uint4*>(in + int64_t(t) * H + vec * 8), x[v]);
+  }
+  warp_layernorm_store<VPL>(x, H, lane, gamma, beta, eps, out + int64_t(t) * H);
+}
+
+// --------------------------------------------------------------- attention
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 16 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// smem tile: ROWS x DH bf16, row = DH*2 bytes split into 16-byte chunks, chunk index XOR-swizzled with
+// the row so that ldmatrix (8 rows x 16 B) is bank-conflict free.
+template <int DH>
+__device__ __forceinline__ __nv_bfloat16* tile_ptr(__nv_bfloat16* base, int row, int chunk) {
+  constexpr int CPR = DH / 8;  // 16-byte chunks per row
+  return base + row * DH + ((chunk ^ (row & (CPR - 1) & 7)) * 8);
+}
+
+template <int DH>
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* smem_tile, const __nv_bfloat16* __restrict__ gbase,
+                                                int64_t row_stride, int row0, int rows_valid, int tid) {
+  constexpr int CPR = DH / 8;
+  constexpr int CHUNKS = 64 * CPR;
+#pragma unroll
+  for (int i = 0; i < CHUNKS / 128; ++i) {
+    const int c = tid + i * 128;
+    const int row = c / CPR, chunk = c % CPR;
+    const bool valid = row0 + row < rows_valid;
+    const __nv_bfloat16* src = gbase + int64_t(valid ? row0 + row : 0) * row_stride + chunk * 8;
+    cp_async_16(tile_ptr<DH>(smem_tile, row, chunk), src, valid);
+  }
+}
+
+// grid = (ceil(max_len/64), heads, n_seqs), block = 128 (4 warps x 16 query rows)
+template <int DH>
+__global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                        const int32_t* __restrict__ cu_seqlens, int H,
+                                                        float scale_log2e, __nv_bfloat16* __restrict__ ctx) {
+  __shared__ __align__(128) __nv_bfloat16 sQ[64 * DH];
+  __shared__ __align__(128) __nv_bfloat16 sK[2][64 * DH];
+  __shared__ __align__(128) __nv_bfloat16 sV[2][64 * DH];
+
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int start = __ldg(cu_seqlens + seq);
+  const int L = __ldg(cu_seqlens + seq + 1) - start;
+  const int q0 = blockIdx.x * 64;
+  if (q0 >= L) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int64_t ld = 3 * int64_t(H);
+  const __nv_bfloat16* qbase = qkv + int64_t(start) * ld + head * DH;
+  const __nv_bfloat16* kbase = qbase + H;
+  const __nv_bfloat16* vbase = qbase + 2 * H;
+  const int n_kv = (L + 63) / 64;
+
+  load_tile_async<DH>(sQ, qbase, ld, q0, L, tid);
+  load_tile_async<DH>(sK[0], kbase, ld, 0, L, tid);
+  load_tile_async<DH>(sV[0], vbase, ld, 0, L, tid);
+  cp_async_commit();
+
+  constexpr int KS = DH / 16;  // k-steps over the head dim
+  constexpr int NT = DH / 8;   // output n-tiles over the head dim
+  uint32_t qf[KS][4];
+  float o[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int j = 0; j < n_kv; ++j) {
+    const int buf = j & 1;
+    if (j + 1 < n_kv) {
+      load_tile_async<DH>(sK[buf ^ 1], kbase, ld, (j + 1) * 64, L, tid);
+      load_tile_async<DH>(sV[buf ^ 1], vbase, ld, (j + 1) * 64, L, tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (j == 0) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        ldmatrix_x4(qf[ks], tile_ptr<DH>(sQ, warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4)));
+    }
+    // S = Q K^T : 16 x 64 per warp
+    float s[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {  // pairs of key n-tiles
+        uint32_t kf[4];
+        // matrices: (keys np*16+0..7, d ks*16+0..7), (same keys, d +8), (keys +8, d 0..7), (keys +8, d +8)
+        ldmatrix_x4(kf, tile_ptr<DH>(sK[buf], np * 16 + (lane & 7) + (lane >> 4) * 8, ks * 2 + ((lane >> 3) & 1)));
+        mma_bf16_16816(s[np * 2], qf[ks], kf[0], kf[1]);
+        mma_bf16_16816(s[np * 2 + 1], qf[ks], kf[2], kf[3]);
+      }
+    }
+    // mask keys beyond the sequence, online softmax (base-2 domain)
+    const int kbase_idx = j * 64;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = kbase_idx + n * 8 + t4 * 2 + (e & 1);
+        float v = s[n][e] * scale_log2e;
+        if (key >= L) v = -INFINITY;
+        s[n][e] = v;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float nm0 = fmaxf(m0, mx0), nm1 = fmaxf(m1, mx1);  // finite: every tile has >= 1 valid key
+    const float c0 = exp2f(m0 - nm0), c1 = exp2f(m1 - nm1);
+    m0 = nm0;
+    m1 = nm1;
+    float rs0 = 0.f, rs1 = 0.f;
+    uint32_t pf[4][4];  // P as A fragments: 4 k-steps of 16 keys
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const float p0 = exp2f(s[n][0] - m0), p1 = exp2f(s[n][1] - m0);
+      const float p2 = exp2f(s[n][2] - m1), p3 = exp2f(s[n][3] - m1);
+      rs0 += p0 + p1;
+      rs1 += p2 + p3;
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+      pf[n >> 1][(n & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&lo);
+      pf[n >> 1][(n & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1;
+    }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
+#pragma unroll
+      for (int dp = 0; dp < NT / 2; ++dp) {  // pairs of d n-tiles
+        uint32_t vf[4];
+        // .trans matrices: (keys kk*16+0..7, d dp*16+0..7), (keys +8, same d), (keys 0..7, d +8), (keys +8, d +8)
+        ldmatrix_x4_trans(vf, tile_ptr<DH>(sV[buf], kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 2 + (lane >> 4)));
+        mma_bf16_16816(o[dp * 2], pf[kk], vf[0], vf[1]);
+        mma_bf16_16816(o[dp * 2 + 1], pf[kk], vf[2], vf[3]);
+      }
+    }
+    __syncthreads();  // all warps done with buf before it is refilled
+  }
+  // row sums live distributed over the 4 lanes of a quad
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const int col = head * DH + n * 8 + t4 * 2;
+    if (r0 < L)
+      *reinterpret_cast<__nv_bfloat162*>(ctx + int64_t(start + r0) * H + col) = __floats2bfloat162_rn(o[n][0] * inv0, o[n][1] * inv0);
+    if (r1 < L)
+      *reinterpret_cast<__nv_bfloat162*>(ctx + int64_t(start + r1) * H + col) = __floats2bfloat162_rn(o[n][2] * inv1, o[n][3] * inv1);
+  }
+}
+
+// ----------------------------------------------------------- pool + normalise
+// one block (128 threads) per sequence; thread owns 8-column vectors
+__global__ void __launch_bounds__(128) pool_normalize_kernel(const __nv_bfloat16* __restrict__ hidden,
+                                                             const int32_t* __restrict__ cu_seqlens, int H,
+                                                             int normalize, float* __restrict__ out_f32,
+                                                             __nv_bfloat16* __restrict__ out_bf16,
+                                                             int64_t out_bf16_stride) {
+  __shared__ float s_part[4];
+  const int seq = blockIdx.x, tid = threadIdx.x;
+  const int start = __ldg(cu_seqlens + seq);
+  const int L = __ldg(cu_seqlens + seq + 1) - start;
+  const int nvec = H / 8;
+  float ss = 0.f;
+  // each thread accumulates up to 2 vectors (H <= 2048)
+  float acc[2][8];
+#pragma unroll
+  for (int v = 0; v < 2; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
+  for (int t = 0; t < L; ++t) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int vec = tid + v * 128;
+      if (vec < nvec) {
+        float f[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(hidden + int64_t(start + t) * H + vec * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[v][j] += f[j];
+      }
+    }
+  }
+  const float inv_len = 1.f / float(L);  // L == 0 -> inf/nan row, as the reference's 0/0 would give
+#pragma unroll
+  for (int v = 0; v < 2; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[v][j] *= inv_len;
+      if (tid + v * 128 < nvec) ss += acc[v][j] * acc[v][j];
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((tid & 31) == 0) s_part[tid >> 5] = ss;
+  __syncthreads();
+  const float norm = sqrtf(s_part[0] + s_part[1] + s_part[2] + s_part[3]);
+  const float inv = normalize ? 1.f / fmaxf(norm, 1e-12f) : 1.f;  // F.normalize eps
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const int vec = tid + v * 128;
+    if (vec < nvec) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = acc[v][j] * inv;
+      if (out_f32) {
+        float4* dst = reinterpret_cast<float4*>(out_f32 + int64_t(seq) * H + vec * 8);
+        dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+        dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+      }
+      if (out_bf16) {
+        __nv_bfloat162 o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(r[2 * j], r[2 * j + 1]);
+        *reinterpret_cast<uint4*>(out_bf16 + int64_t(seq) * out_bf16_stride + vec * 8) = *reinterpret_cast<uint4*>(o);
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------- launchers
+int launch_embed_layernorm(const int32_t* token_ids, const int32_t* cu_seqlens, int n_seqs, int T, int H, int vocab,
+                           int max_pos, int pos_offset, const void* word_emb, const void* pos_emb,
+                           const void* type_emb, const float* gamma, const float* beta, float eps, void* out,
+                           cudaStream_t stream) {
+  if (T <= 0) return CRAG_OK;
+  const int grid = (T + 3) / 4;
+  const auto* we = static_cast<const __nv_bfloat16*>(word_emb);
+  const auto* pe = static_cast<const __nv_bfloat16*>(pos_emb);
+  const auto* te = static_cast<const __nv_bfloat16*>(type_emb);
+  auto* o = static_cast<__nv_bfloat16*>(out);
+  const int vpl = (H / 8 + 31) / 32;
+  if (vpl <= 1) embed_layernorm_kernel<1><<<grid, 128, 0, stream>>>(token_ids, cu_seqlens, n_seqs, T, H, vocab, max_pos, pos_offset, we, pe, te, gamma, beta, eps, o);
+  else if (vpl <= 2) embed_layernorm_kernel<2><<<grid, 128, 0, stream>>>(token_ids, cu_seqlens, n_seqs, T, H, vocab, max_pos, pos_offset, we, pe, te, gamma, beta, eps, o);
+  else if (vpl <= 4) embed_layernorm_kernel<4><<<grid, 128, 0, stream>>>(token_ids, cu_seqlens, n_seqs, T, H, vocab, max_pos, pos_offset, we, pe, te, gamma, beta, eps, o);
+  else return fail(CRAG_ERR_UNSUPPORTED, "hidden size %d > 1024 not supported", H);
+  CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
+}
+
+int launch_layernorm(const void* in, int T, int H, const float* gamma, const float* beta, float eps, void* out,
+                     cudaStream_t stream) {
+  if (T <= 0) return CRAG_OK;
+  const int grid = (T + 3) / 4;
+  const auto* i = static_cast<const __nv_bfloat16*>(in);
+  auto* o = static_cast<__nv_bfloat16*>(out);
+  const int vpl = (H / 8 + 31) / 32;
+  if (vpl <= 1) layernorm_kernel<1><<<grid, 128, 0, stream>>>(i, T, H, gamma, beta, eps, o);
+  else if (vpl <= 2) layernorm_kernel<2><<<grid, 128, 0, stream>>>(i, T, H, gamma, beta, eps, o);
+  else if (vpl <= 4) layernorm_kernel<4><<<grid, 128, 0, stream>>>(i, T, H, gamma, beta, eps, o);
+  else return fail(CRAG_ERR_UNSUPPORTED, "hidden size %d > 1024 not supported", H);
+  CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
+}
+
+int launch_attention(const void* qkv, const int32_t* cu_seqlens, int n_seqs, int max_len, int H, int heads, void* ctx,
+                     cudaStream_t stream) {
+  if (n_seqs <= 0 || max_len <= 0) return CRAG_OK;
+  const int dh = H / heads;
+  const dim3 grid((max_len + 63) / 64, heads, n_seqs);
+  const float scale_log2e = 1.4426950408889634f / sqrtf(float(dh));
+  const auto* q = static_cast<const __nv_bfloat16*>(qkv);
+  auto* c = static_cast<__nv_bfloat16*>(ctx);
+  if (dh == 64) attention_kernel<64><<<grid, 128, 0, stream>>>(q, cu_seqlens, H, scale_log2e, c);
+  else if (dh == 32) attention_kernel<32><<<grid, 128, 0, stream>>>(q, cu_seqlens, H, scale_log2e, c);
+  else return fail(CRAG_ERR_UNSUPPORTED, "head dim %d not supported (32 or 64)", dh);
+  CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
+}
+
+int launch_pool_normalize(const void* hidden, const int32_t* cu_seqlens, int n_seqs, int H, int normalize,
+                          float* out_f32, void* out_bf16, int64_t out_bf16_stride, cudaStream_t stream) {
+  if (n_seqs <= 0) return CRAG_OK;
+  if (H > 2048) return fail(CRAG_ERR_UNSUPPORTED, "hidden size %d > 2048 not supported", H);
+  pool_normalize_kernel<<<n_seqs, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(hidden), cu_seqlens, H, normalize,
+                                                    out_f32, static_cast<__nv_bfloat16*>(out_bf16), out_bf16_stride);
+  CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
+}
+
+}  // namespace crag

@@ -102,6 +102,28 @@ CRAG_API int crag_search_topk(const void* corpus, int64_t n_rows, int dim, int64
 CRAG_API int crag_merge_topk(const float* scores, const int64_t* ids, const float* minmax, int parts, int nq, int k,
                     int64_t* out_ids, float* out_scores, float* out_minmax, crag_stream_t stream);
 
+/* ------------------------------------------------------------------ encoder
+ * Dense projection of the encoder forward (BGEEmbedding.py:120 runs it through
+ * HF's BertModel: attention.self.{query,key,value}, attention.output.dense,
+ * intermediate.dense (+ exact-erf GELU), output.dense), torch.nn.Linear layout:
+ *
+ *     out[m, n] = epilogue( sum_k a[m, k] * w[n, k] + bias[n] )
+ *
+ *   a         device bf16 [m, k], leading dimension lda (elements)
+ *   w         device bf16 [n, k], leading dimension ldw
+ *   bias      device fp32 [n]
+ *   residual  device bf16 [m, n] (ldr), only for CRAG_GEMM_BIAS_RESIDUAL
+ *   out       device bf16 [m, n] (ldo)
+ * n, k, and all leading dimensions must be multiples of 8; pointers 16-B aligned.
+ * Accumulation is fp32 on the tcgen05 tensor cores.
+ */
+#define CRAG_GEMM_BIAS 0          /* out = acc + bias */
+#define CRAG_GEMM_BIAS_GELU 1     /* out = gelu_erf(acc + bias) */
+#define CRAG_GEMM_BIAS_RESIDUAL 2 /* out = acc + bias + residual */
+CRAG_API int crag_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias,
+                            const void* residual, int64_t ldr, void* out, int64_t ldo, int m, int n, int k,
+                            int epilogue, crag_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
