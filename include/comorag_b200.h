@@ -124,6 +124,86 @@ CRAG_API int crag_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
                             const void* residual, int64_t ldr, void* out, int64_t ldo, int m, int n, int k,
                             int epilogue, crag_stream_t stream);
 
+/* Encoder weights (BERT-family, post-LN; HF BertModel parameter names in
+ * comments).  Matrices are device bf16 in torch.nn.Linear layout [out, in];
+ * biases and LayerNorm parameters are device fp32.  The struct itself and the
+ * layer table are HOST memory. */
+typedef struct crag_encoder_layer {
+  const void* w_qkv;   /* [3H, H]: attention.self.{query,key,value}.weight stacked */
+  const float* b_qkv;  /* [3H] */
+  const void* w_o;     /* [H, H]: attention.output.dense.weight */
+  const float* b_o;    /* [H] */
+  const float* ln1_g;  /* attention.output.LayerNorm.weight */
+  const float* ln1_b;
+  const void* w_ff1;   /* [I, H]: intermediate.dense.weight */
+  const float* b_ff1;  /* [I] */
+  const void* w_ff2;   /* [H, I]: output.dense.weight */
+  const float* b_ff2;  /* [H] */
+  const float* ln2_g;  /* output.LayerNorm.weight */
+  const float* ln2_b;
+} crag_encoder_layer;
+
+typedef struct crag_encoder {
+  int32_t hidden;        /* H: 64..1024, multiple of 8; H / heads in {32, 64} */
+  int32_t n_layers;
+  int32_t heads;
+  int32_t intermediate;  /* I */
+  int32_t vocab;
+  int32_t max_pos;       /* rows of the position table */
+  int32_t pos_offset;    /* 0 for BERT, padding_idx + 1 (= 2) for XLM-R */
+  float ln_eps;          /* 1e-12 for BERT */
+  const void* word_emb;  /* bf16 [vocab, H] */
+  const void* pos_emb;   /* bf16 [max_pos, H] */
+  const void* type_emb;  /* bf16 [>=1, H]; row 0 is used (token_type_ids == 0) */
+  const float* emb_ln_g;
+  const float* emb_ln_b;
+  const crag_encoder_layer* layers; /* host array [n_layers] */
+} crag_encoder;
+
+/* Encoder forward + masked mean pool + L2 normalise for a packed batch.
+ *
+ * Replaces BGEEmbeddingModel._encode's device work (BGEEmbedding.py:119-127):
+ * outputs = model(**inputs); mean_pooling(last_hidden_state, attention_mask)
+ * (BGEEmbedding.py:15-28); F.normalize(p=2, dim=1).  Sequences are packed
+ * without padding: token_ids[total_tokens], sequence i owns
+ * [cu_seqlens[i], cu_seqlens[i+1]).
+ *
+ *   token_ids    device int32 [total_tokens]
+ *   cu_seqlens   device int32 [n_seqs + 1], cu_seqlens[0] = 0
+ *   max_seqlen   longest sequence in the batch (host value, sizes the grid)
+ *   normalize    1 = L2-normalise rows (the reference default), 0 = raw mean
+ *   out_f32      device fp32 [n_seqs, H] or NULL
+ *   out_bf16     device bf16 rows with stride out_bf16_stride elements, or NULL
+ *                (lets index build write straight into the corpus shard)
+ *   workspace    >= crag_encoder_workspace_bytes(model, total_tokens), 256-B aligned
+ */
+CRAG_API size_t crag_encoder_workspace_bytes(const crag_encoder* model, int total_tokens);
+CRAG_API int crag_encoder_forward(const crag_encoder* model, const int32_t* token_ids, const int32_t* cu_seqlens,
+                                  int n_seqs, int total_tokens, int max_seqlen, int normalize, float* out_f32,
+                                  void* out_bf16, int64_t out_bf16_stride, void* workspace, size_t workspace_bytes,
+                                  crag_stream_t stream);
+
+/* K3 on its own: masked mean pool + optional L2 normalise of a packed
+ * last_hidden_state (bf16 [total_tokens, hidden_size]); mean_pooling
+ * (BGEEmbedding.py:15-28) + F.normalize (:127). */
+CRAG_API int crag_pool_normalize(const void* hidden, const int32_t* cu_seqlens, int n_seqs, int hidden_size,
+                                 int normalize, float* out_f32, void* out_bf16, int64_t out_bf16_stride,
+                                 crag_stream_t stream);
+
+/* K2 on its own: varlen multi-head self-attention over a packed batch, as HF's
+ * BertSelfAttention computes it (softmax(q k^T / sqrt(dh)) v, keys restricted
+ * to the token's own sequence == the reference's key-padding mask).
+ *   qkv  device bf16 [total_tokens, 3*hidden] = [q | k | v], heads contiguous
+ *   ctx  device bf16 [total_tokens, hidden]
+ * hidden/heads must be 32 or 64. */
+CRAG_API int crag_attention_varlen(const void* qkv, const int32_t* cu_seqlens, int n_seqs, int max_seqlen,
+                                   int hidden_size, int heads, void* ctx, crag_stream_t stream);
+
+/* torch.nn.LayerNorm over the last dimension, bf16 in/out, fp32 statistics
+ * (BertSelfOutput / BertOutput LayerNorm). hidden_size <= 1024, multiple of 8. */
+CRAG_API int crag_layernorm(const void* in, int rows, int hidden_size, const float* gamma, const float* beta,
+                            float eps, void* out, crag_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
