@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of BASELINE.json on B200: brute-force IP top-10 over a 10M x 1024 bf16 index
+(queries/sec) and BGE-large index-build encode (chunks/sec).
+
+    python bench.py [--gpus N --steps K --warmup W]            # our arm, one JSON line on stdout
+    python bench.py --impl reference [...]                     # the reference's CPU path, same metric
+    torchrun --nproc-per-node N bench.py --gpus N ...          # N > 1: one rank per GPU (launched by the driver)
+
+A "step" is one pass of the search hot path over one batch of 32 synthetic probe queries (config 5's probe
+batch) against the whole index: N=1 holds all 10M rows on one GPU (20.5 GB bf16); at N>1 the SAME 10M rows are
+row-sharded over the ranks ("strong" scaling: total work fixed), each step = local fused scan + ONE
+all-gather + merge kernel.  `value` = queries/sec with queries already in HBM; `e2e` = the same through the
+public host API (pinned fp32 queries -> H2D -> search -> D2H of ids/scores/minmax, every step).  The `encode`
+object times the index-build encoder (BGE-large shape, random-init weights, 32 chunks x 512 tokens per
+rank per step; data-parallel, no collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000, help="total index rows (BASELINE: 10M)")
+    ap.add_argument("--dim", type=int, default=1024)
+    ap.add_argument("--nq", type=int, default=32, help="probe queries per step")
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--encode-chunks", type=int, default=32, help="chunks per encode step per rank")
+    ap.add_argument("--encode-len", type=int, default=512)
+    ap.add_argument("--encode-steps", type=int, default=5)
+    ap.add_argument("--no-encode", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU baseline sample budget (seconds)")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        load = [c for c in sm if c > 0.5 * (mx[0] if mx else 1)] or sm
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx[0] if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ CPU baseline
+class CpuSearch:
+    """The reference's per-query CPU search (oracle port of ComoRAG.py:950-967: np.dot -> min_max_normalize ->
+    full np.argsort[::-1]) on this host, one query at a time as the reference does, all BLAS threads.
+
+    Sample: an fp32 [rows, dim] slab (rows <= full_rows, bounded by free RAM and the time budget); q/s is
+    scaled to full_rows by the row ratio (the dot is linear in N; the argsort's extra log factor is ignored,
+    which flatters the CPU side slightly).
+    """
+
+    def __init__(self, rows: int, dim: int, full_rows: int):
+        import torch
+        g = torch.Generator().manual_seed(1234)
+        t0 = time.time()
+        x = torch.randn(rows, dim, generator=g)
+        x /= x.norm(dim=1, keepdim=True)
+        self.mat = x.numpy()
+        self.q = torch.nn.functional.normalize(torch.randn(8, dim, generator=g), dim=1).numpy()
+        self.gen_s = time.time() - t0
+        self.rows, self.dim, self.full_rows = rows, dim, full_rows
+        self.i = 0
+        self.query(1)  # warm
+
+    def query(self, n: int):
+        from oracle import search_oracle
+        times = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            ids, sc = search_oracle.dense_passage_retrieval(self.mat, self.q[self.i % 8: self.i % 8 + 1])
+            times.append(time.perf_counter() - t0)
+            self.i += 1
+        return times
+
+    def describe(self, times) -> dict:
+        import numpy as np
+        import torch
+        per_query = float(np.median(times))
+        scale = self.full_rows / self.rows
+        return {"value": 1.0 / (per_query * scale), "unit": UNIT, "cores": os.cpu_count(), "threads": torch.get_num_threads(),
+                "kind": "port",
+                "sample": f"{len(times)} single queries over an fp32 [{self.rows}, {self.dim}] slab (gen {self.gen_s:.1f}s), "
+                          f"median {per_query * 1e3:.1f} ms/query, scaled x{scale:g} rows to {self.full_rows}"}
+
+
+def cpu_search_baseline(rows: int, dim: int, k: int, budget_s: float, full_rows: int):
+    cs = CpuSearch(rows, dim, full_rows)
+    times, t0 = [], time.time()
+    while (time.time() - t0 < budget_s and len(times) < 64) or len(times) < 2:
+        times += cs.query(1)
+    return cs.describe(times)
+
+
+def cpu_encode_baseline(cfg_name: str, n_chunks: int, seq_len: int):
+    """The reference's encode path on CPU: HF BertModel fp32 forward + mean pool + normalise
+    (BGEEmbedding.py:119-127) on random-init weights of the same shape, all host threads."""
+    import torch
+    from transformers import BertConfig, BertModel
+    from comorag_b200.encoder import EncoderConfig
+    from oracle.encoder_oracle import mean_pooling
+    cfg = getattr(EncoderConfig, cfg_name)()
+    hf = BertModel(BertConfig(hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_hidden_layers,
+                              num_attention_heads=cfg.num_attention_heads, intermediate_size=cfg.intermediate_size,
+                              vocab_size=cfg.vocab_size), add_pooling_layer=False).eval()
+    ids = torch.randint(1000, cfg.vocab_size, (n_chunks, seq_len))
+    mask = torch.ones_like(ids)
+    with torch.no_grad():
+        hf(input_ids=ids[:1, :64], attention_mask=mask[:1, :64])
+        t0 = time.perf_counter()
+        out = hf(input_ids=ids, attention_mask=mask).last_hidden_state
+        torch.nn.functional.normalize(mean_pooling(out, mask), dim=1)
+        dt = time.perf_counter() - t0
+    return {"value": n_chunks / dt, "unit": "chunks/s", "cores": os.cpu_count(), "threads": torch.get_num_threads(),
+            "kind": "reference-library", "sample": f"one HF BertModel fp32 forward of {n_chunks} x {seq_len} tokens ({dt:.2f}s)"}
+
+
+def pick_cpu_rows(full_rows: int, dim: int, budget_s: float) -> int:
+    try:
+        import psutil
+        free = psutil.virtual_memory().available
+    except Exception:
+        free = 16 << 30
+    # ~0.35 s per query per 1M x 1024 rows on 8 cores; keep generation + a few queries inside the budget
+    by_time = int(500_000 * max(budget_s / 20.0, 0.25))
+    by_mem = int(free * 0.4 / (dim * 4 * 2.5))
+    return max(50_000, min(full_rows, by_time, by_mem))
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """--impl reference: the reference's own CPU path for the same metric/config, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = time.time()
+    rows = min(pick_cpu_rows(args.rows, args.dim, 40.0), 1_000_000)
+    cs = CpuSearch(rows, args.dim, args.rows)
+    per_step = 2  # queries per step (the reference scores one query at a time; a step samples 2 of the 32)
+    for _ in range(args.warmup):
+        cs.query(per_step)
+    times = []
+    for _ in range(args.steps):
+        times += cs.query(per_step)
+    base = cs.describe(times)
+    value = base["value"]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": args.nq / value * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.rows}x{args.dim} IP top-{args.k}, {args.nq} probe queries per step "
+                                   f"(reference CPU path: per-query np.dot + min-max + full argsort)",
+                       "index_rows": args.rows, "dim": args.dim, "queries_per_step": args.nq, "k": args.k},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def make_shard(rows: int, dim: int, seed: int, device):
+    """Seeded unit-norm rows rounded to bf16, generated on the device in slabs."""
+    import torch
+    out = torch.empty((rows, dim), dtype=torch.bfloat16, device=device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    slab = 1 << 19
+    for s in range(0, rows, slab):
+        n = min(slab, rows - s)
+        x = torch.randn((n, dim), generator=g, device=device, dtype=torch.float32)
+        out[s:s + n] = torch.nn.functional.normalize(x, dim=1).to(torch.bfloat16)
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from comorag_b200 import _native
+    from comorag_b200.dist import ShardedIndex, shard_bounds
+    from comorag_b200.index import DenseIndex
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (ours) needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.load()
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- index: the same 10M rows at every N, row-sharded (strong scaling)
+    offs = shard_bounds(args.rows, world)
+    my_rows = offs[rank + 1] - offs[rank]
+    corpus = make_shard(my_rows, args.dim, 1234 + rank, dev)
+    index = ShardedIndex(DenseIndex.from_tensor(corpus, row_offset=offs[rank]))
+    gq = torch.Generator().manual_seed(4321)
+    q_host = torch.nn.functional.normalize(torch.randn(args.nq, args.dim, generator=gq), dim=1).pin_memory()
+    q_dev = q_host.to(dev).to(torch.bfloat16).contiguous()
+    st = torch.cuda.current_stream(dev)
+
+    def step_device():
+        return index.search_device(q_dev, args.k)
+
+    def step_e2e():
+        q = q_host.to(dev, non_blocking=True).to(torch.bfloat16)
+        ids, scores, mm = index.search_device(q, args.k)
+        out = (ids.cpu(), scores.cpu(), mm.cpu())  # D2H of the step's result; .cpu() synchronises
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(st)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(st)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms_total / args.steps
+    value = args.nq / ms_per_step * 1e3
+
+    # ---- roofline of the dominant kernel: the shard scan, timed alone with CUDA events on its stream
+    ws_bytes = lib.crag_search_workspace_bytes(args.nq, args.k)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    scan_ms = []
+    for i in range(args.steps + 3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        rc = lib.crag_search_scan(corpus.data_ptr(), my_rows, args.dim, corpus.stride(0), q_dev.data_ptr(), args.nq, args.k,
+                                  ws.data_ptr(), ws_bytes, st.cuda_stream)
+        b.record(st)
+        _native.check(rc, "crag_search_scan")
+        torch.cuda.synchronize()
+        if i >= 3:
+            scan_ms.append(a.elapsed_time(b))
+    scan_avg = sum(scan_ms) / len(scan_ms)
+    algo_bytes = float(my_rows) * args.dim * 2
+    achieved = algo_bytes / scan_avg / 1e6  # GB/s
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e through the host API
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = args.nq * args.steps / e2e_s
+    h2d = args.nq * args.dim * 4
+    d2h = args.nq * args.k * (8 + 4) + args.nq * 2 * 4
+
+    # ---- encode (index build): data-parallel, every rank encodes its own batch
+    encode = None
+    if not args.no_encode:
+        from comorag_b200.encoder import BertEncoderB200, EncoderConfig
+        cfg = EncoderConfig.bge_large()
+        enc = BertEncoderB200.random_init(cfg, seed=0, device=dev)
+        n, L = args.encode_chunks, args.encode_len
+        gi = torch.Generator().manual_seed(99 + rank)
+        ids_host = torch.randint(1000, cfg.vocab_size, (n * L,), generator=gi, dtype=torch.int32).pin_memory()
+        cu_host = (torch.arange(n + 1, dtype=torch.int32) * L).pin_memory()
+        ids_dev, cu_dev = ids_host.to(dev), cu_host.to(dev)
+        out = torch.empty((n, cfg.hidden_size), dtype=torch.float32, device=dev)
+        for _ in range(3):
+            enc.forward_packed(ids_dev, cu_dev, L, out_f32=out)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for _ in range(args.encode_steps):
+            enc.forward_packed(ids_dev, cu_dev, L, out_f32=out)
+        b.record(st)
+        barrier()
+        enc_ms = max_over_ranks(a.elapsed_time(b)) / args.encode_steps
+        chunks_s = world * n / enc_ms * 1e3
+        flops = cfg.flops_per_chunk(L) * n
+        enc_tflops = flops / enc_ms / 1e9
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.encode_steps):
+            o = enc.forward_packed(ids_host.to(dev, non_blocking=True), cu_host.to(dev, non_blocking=True), L)
+            o.cpu()
+        e2e_enc_s = max_over_ranks(time.perf_counter() - t0)
+        encode = {"metric": "encode chunks/sec", "value": chunks_s, "unit": "chunks/s", "ms_per_step": enc_ms,
+                  "config": {"workload": f"bge-large-en-v1.5 shape (1024-d, 24 layers), {n} chunks x {L} tokens per rank per step, random-init bf16 weights",
+                             "scaling": "weak (data-parallel, no collective)"},
+                  "dtype": "bf16",
+                  "e2e": {"value": world * n * args.encode_steps / e2e_enc_s, "unit": "chunks/s",
+                          "h2d_bytes_per_step": n * L * 4 + (n + 1) * 4, "d2h_bytes_per_step": n * cfg.hidden_size * 4},
+                  "roofline": {"bound": "tensor", "achieved": enc_tflops, "peak": peaks["bf16_tflops_sustained"],
+                               "unit": "TFLOP/s", "frac": enc_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+                               "peak_source": peaks["source"] + " (sustained)", "flops_per_chunk": cfg.flops_per_chunk(L)},
+                  "gpu_launches": args.encode_steps * (2 + cfg.num_hidden_layers * 7)}
+        del enc
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rows = pick_cpu_rows(args.rows, args.dim, args.cpu_budget_s)
+        cpu = cpu_search_baseline(rows, args.dim, args.k, args.cpu_budget_s * 0.5, args.rows)
+        if encode is not None:
+            try:
+                encode["cpu_baseline"] = cpu_encode_baseline("bge_large", 4, args.encode_len)
+            except Exception as e:  # transformers missing etc.: report, do not fake
+                encode["cpu_baseline"] = {"unavailable": repr(e)[:200]}
+
+    if rank == 0:
+        launches_per_step = 2 + (1 if world > 1 else 0)  # scan + per-shard merge (+ cross-rank merge)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.rows}x{args.dim} bf16 index, brute-force IP top-{args.k}, {args.nq} probe queries per step, "
+                                   f"row-sharded over {world} GPU(s)" + (" + one NCCL all-gather + merge" if world > 1 else ""),
+                       "index_rows": args.rows, "rows_per_rank": my_rows, "dim": args.dim, "queries_per_step": args.nq, "k": args.k,
+                       "l2": f"inputs larger than L2 ({algo_bytes / 1e9:.2f} GB shard per rank vs 126 MB)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": args.steps * launches_per_step,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                         "kernel": "search_topk_kernel", "algorithmic_bytes_per_launch": algo_bytes,
+                         "kernel_ms": scan_avg},
+            "cpu_baseline": cpu,
+            "encode": encode,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -395,49 +395,98 @@ extern "C" size_t crag_search_workspace_bytes(int nq, int k) {
   return p.keys_bytes + p.minmax_bytes;
 }
 
+namespace crag {
+namespace {
+
+int check_search_args(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride, const void* queries,
+                      int nq, int k, const void* workspace, size_t workspace_bytes, const SearchPlan& plan) {
+  if (nq < 1 || k < 1 || k > 128) return fail(CRAG_ERR_INVALID, "search: need nq >= 1 and 1 <= k <= 128 (nq=%d k=%d)", nq, k);
+  if (dim < 64 || dim > 1024 || dim % 64 != 0) return fail(CRAG_ERR_INVALID, "search: dim must be a multiple of 64 in [64, 1024] (dim=%d)", dim);
+  if (n_rows < 0 || n_rows >= (int64_t(1) << 31) - kTileRows) return fail(CRAG_ERR_INVALID, "search: n_rows out of range (%lld)", (long long)n_rows);
+  if (corpus_row_stride < dim || corpus_row_stride % 8 != 0) return fail(CRAG_ERR_INVALID, "search: corpus_row_stride must be >= dim and a multiple of 8");
+  if (!queries || !workspace || (n_rows > 0 && !corpus)) return fail(CRAG_ERR_INVALID, "search: null pointer");
+  if ((reinterpret_cast<uintptr_t>(corpus) | reinterpret_cast<uintptr_t>(queries)) & 15) return fail(CRAG_ERR_INVALID, "search: corpus/queries must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(CRAG_ERR_INVALID, "search: workspace must be 256-byte aligned");
+  if (workspace_bytes < plan.keys_bytes + plan.minmax_bytes) return fail(CRAG_ERR_WORKSPACE, "search: workspace %zu < %zu bytes", workspace_bytes, plan.keys_bytes + plan.minmax_bytes);
+  return CRAG_OK;
+}
+
+inline int scan_grid(int64_t n_rows, const SearchPlan& plan) {
+  const int num_tiles = int((n_rows + kTileRows - 1) / kTileRows);
+  return num_tiles < plan.grid ? num_tiles : plan.grid;
+}
+
+// one corpus pass for <= 32 queries: per-CTA partial lists into the workspace
+int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride, const void* queries, int nq,
+              int k, void* workspace, const SearchPlan& plan, cudaStream_t stream) {
+  const int grid = scan_grid(n_rows, plan);
+  if (grid == 0) return CRAG_OK;
+  uint64_t* part_keys = static_cast<uint64_t*>(workspace);
+  float* part_minmax = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes);
+  CUtensorMap tm_corpus, tm_q;
+  int rc = make_tmap_bf16_2d(&tm_corpus, corpus, uint64_t(n_rows), uint64_t(dim), uint64_t(corpus_row_stride) * 2, kTileRows);
+  if (rc != CRAG_OK) return rc;
+  rc = make_tmap_bf16_2d(&tm_q, queries, uint64_t(nq), uint64_t(dim), uint64_t(dim) * 2, kNQ);
+  if (rc != CRAG_OK) return rc;
+  const int num_kb = dim / kBlockK;
+  if (k <= 64) return launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, part_keys, part_minmax, stream);
+  return launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, part_keys, part_minmax, stream);
+}
+
+// merge the per-CTA partials of one pass into the final (ids, scores, minmax) of its <= 32 queries
+int finalize_pass(const void* workspace, int64_t n_rows, int nq, int k, int64_t row_offset, int64_t* out_ids,
+                  float* out_scores, float* out_minmax, const SearchPlan& plan, cudaStream_t stream) {
+  const int grid = scan_grid(n_rows, plan);
+  const uint64_t* part_keys = static_cast<const uint64_t*>(workspace);
+  const float* part_minmax = reinterpret_cast<const float*>(static_cast<const uint8_t*>(workspace) + plan.keys_bytes);
+  const int mgrid = (nq + 3) / 4;
+  if (k <= 64)
+    merge_topk_kernel<64, 64, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, out_ids, out_scores, out_minmax);
+  else
+    merge_topk_kernel<128, 128, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, out_ids, out_scores, out_minmax);
+  CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
+}
+
+}  // namespace
+}  // namespace crag
+
+extern "C" int crag_search_scan(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride,
+                                const void* queries, int nq, int k, void* workspace, size_t workspace_bytes,
+                                crag_stream_t stream) {
+  const SearchPlan plan = plan_search(k >= 1 && k <= 128 ? k : 1);
+  int rc = check_search_args(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, workspace, workspace_bytes, plan);
+  if (rc != CRAG_OK) return rc;
+  if (nq > kNQ) return fail(CRAG_ERR_INVALID, "crag_search_scan handles one pass of at most %d queries (nq=%d)", kNQ, nq);
+  return scan_pass(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, workspace, plan, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int crag_search_finalize(const void* workspace, size_t workspace_bytes, int64_t n_rows, int nq, int k,
+                                    int64_t row_offset, int64_t* out_ids, float* out_scores, float* out_minmax,
+                                    crag_stream_t stream) {
+  if (nq < 1 || nq > kNQ || k < 1 || k > 128) return fail(CRAG_ERR_INVALID, "crag_search_finalize: bad nq/k (nq=%d k=%d)", nq, k);
+  const SearchPlan plan = plan_search(k);
+  if (!workspace || !out_ids || !out_scores) return fail(CRAG_ERR_INVALID, "crag_search_finalize: null pointer");
+  if (workspace_bytes < plan.keys_bytes + plan.minmax_bytes) return fail(CRAG_ERR_WORKSPACE, "crag_search_finalize: workspace too small");
+  return finalize_pass(workspace, n_rows, nq, k, row_offset, out_ids, out_scores, out_minmax, plan, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int crag_search_topk(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride,
                                 int64_t row_offset, const void* queries, int nq, int k, int64_t* out_ids,
                                 float* out_scores, float* out_minmax, void* workspace, size_t workspace_bytes,
                                 crag_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (nq < 1 || k < 1 || k > 128) return fail(CRAG_ERR_INVALID, "crag_search_topk: need nq >= 1 and 1 <= k <= 128 (nq=%d k=%d)", nq, k);
-  if (dim < 64 || dim > 1024 || dim % 64 != 0) return fail(CRAG_ERR_INVALID, "crag_search_topk: dim must be a multiple of 64 in [64, 1024] (dim=%d)", dim);
-  if (n_rows < 0 || n_rows >= (int64_t(1) << 31) - kTileRows) return fail(CRAG_ERR_INVALID, "crag_search_topk: n_rows out of range (%lld)", (long long)n_rows);
-  if (corpus_row_stride < dim || corpus_row_stride % 8 != 0) return fail(CRAG_ERR_INVALID, "crag_search_topk: corpus_row_stride must be >= dim and a multiple of 8");
-  if (!queries || !out_ids || !out_scores || !workspace || (n_rows > 0 && !corpus)) return fail(CRAG_ERR_INVALID, "crag_search_topk: null pointer");
-  if ((reinterpret_cast<uintptr_t>(corpus) | reinterpret_cast<uintptr_t>(queries)) & 15) return fail(CRAG_ERR_INVALID, "crag_search_topk: corpus/queries must be 16-byte aligned");
-  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(CRAG_ERR_INVALID, "crag_search_topk: workspace must be 256-byte aligned");
-  const SearchPlan plan = plan_search(k);
-  if (workspace_bytes < plan.keys_bytes + plan.minmax_bytes) return fail(CRAG_ERR_WORKSPACE, "crag_search_topk: workspace %zu < %zu bytes", workspace_bytes, plan.keys_bytes + plan.minmax_bytes);
-
-  uint64_t* part_keys = static_cast<uint64_t*>(workspace);
-  float* part_minmax = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes);
-  const int num_kb = dim / kBlockK;
-  const int num_tiles = int((n_rows + kTileRows - 1) / kTileRows);
-  const int grid = num_tiles < plan.grid ? num_tiles : plan.grid;
-
-  CUtensorMap tm_corpus;
-  if (n_rows > 0) {
-    int rc = make_tmap_bf16_2d(&tm_corpus, corpus, uint64_t(n_rows), uint64_t(dim), uint64_t(corpus_row_stride) * 2, kTileRows);
-    if (rc != CRAG_OK) return rc;
-  }
+  const SearchPlan plan = plan_search(k >= 1 && k <= 128 ? k : 1);
+  int rc = check_search_args(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, workspace, workspace_bytes, plan);
+  if (rc != CRAG_OK) return rc;
+  if (!out_ids || !out_scores) return fail(CRAG_ERR_INVALID, "search: null output pointer");
   for (int q0 = 0; q0 < nq; q0 += kNQ) {
     const int nqc = (nq - q0) < kNQ ? (nq - q0) : kNQ;
-    if (grid > 0) {
-      CUtensorMap tm_q;
-      int rc = make_tmap_bf16_2d(&tm_q, static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2, uint64_t(nqc), uint64_t(dim), uint64_t(dim) * 2, kNQ);
-      if (rc != CRAG_OK) return rc;
-      if (k <= 64) rc = launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nqc, k, grid, part_keys, part_minmax, stream);
-      else rc = launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nqc, k, grid, part_keys, part_minmax, stream);
-      if (rc != CRAG_OK) return rc;
-    }
-    const int mgrid = (nqc + 3) / 4;
-    float* omm = out_minmax ? out_minmax + size_t(q0) * 2 : nullptr;
-    if (k <= 64)
-      merge_topk_kernel<64, 64, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nqc, k, row_offset, out_ids + size_t(q0) * k, out_scores + size_t(q0) * k, omm);
-    else
-      merge_topk_kernel<128, 128, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nqc, k, row_offset, out_ids + size_t(q0) * k, out_scores + size_t(q0) * k, omm);
-    CRAG_CUDA_OK(cudaGetLastError());
+    rc = scan_pass(corpus, n_rows, dim, corpus_row_stride, static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2, nqc, k, workspace, plan, stream);
+    if (rc != CRAG_OK) return rc;
+    rc = finalize_pass(workspace, n_rows, nqc, k, row_offset, out_ids + size_t(q0) * k, out_scores + size_t(q0) * k,
+                       out_minmax ? out_minmax + size_t(q0) * 2 : nullptr, plan, stream);
+    if (rc != CRAG_OK) return rc;
   }
   return CRAG_OK;
 }

@@ -1,0 +1,76 @@
+"""Row-sharded index across the GPUs of one box: one process per GPU (torch.distributed), each rank scans
+its own shard with the fused kernel, ONE all-gather of the packed per-rank (ids, scores, min/max) and a
+merge kernel give every rank the global top-k.
+
+Rank r owns global rows [offsets[r], offsets[r+1]); ids written by the shard kernel are already global.
+The reference has no distributed code -- this is the exchange step the shard layout adds.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_rows: int, world: int) -> List[int]:
+    """Contiguous, near-equal row blocks: offsets[r] .. offsets[r+1] for rank r (first n % world ranks get one more)."""
+    base, rem = divmod(int(n_rows), int(world))
+    offs = [0]
+    for r in range(world):
+        offs.append(offs[-1] + base + (1 if r < rem else 0))
+    return offs
+
+
+def pack_partial(ids: torch.Tensor, scores: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:
+    """(int64 [nq,k], fp32 [nq,k], fp32 [nq,2]) -> one contiguous uint8 buffer (a single collective payload)."""
+    return torch.cat([ids.contiguous().view(torch.uint8).reshape(-1), scores.contiguous().view(torch.uint8).reshape(-1),
+                      minmax.contiguous().view(torch.uint8).reshape(-1)])
+
+
+def unpack_partials(buf: torch.Tensor, world: int, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """[world * bytes] uint8 -> ids int64 [world,nq,k], scores fp32 [world,nq,k], minmax fp32 [world,nq,2]."""
+    per = nq * k * 8 + nq * k * 4 + nq * 2 * 4
+    b = buf.view(world, per)
+    a, c = nq * k * 8, nq * k * 8 + nq * k * 4
+    ids = b[:, :a].contiguous().view(torch.int64).view(world, nq, k)
+    scores = b[:, a:c].contiguous().view(torch.float32).view(world, nq, k)
+    minmax = b[:, c:].contiguous().view(torch.float32).view(world, nq, 2)
+    return ids, scores, minmax
+
+
+def merge_partials_reference(ids: torch.Tensor, scores: torch.Tensor, minmax: torch.Tensor, k: int):
+    """Plain-torch statement of the merge rule (score desc, then (rank, position) asc) used by the CPU/gloo
+    tests of the exchange step; the product path runs crag_merge_topk on the device."""
+    world, nq, kk = scores.shape
+    s = scores.permute(1, 0, 2).reshape(nq, world * kk).clone()
+    i = ids.permute(1, 0, 2).reshape(nq, world * kk)
+    s[i < 0] = float("-inf")
+    order = torch.argsort(s, dim=1, descending=True, stable=True)[:, :k]
+    out_s, out_i = torch.gather(s, 1, order), torch.gather(i, 1, order)
+    out_i = torch.where(torch.isinf(out_s) & (out_s < 0), torch.full_like(out_i, -1), out_i)
+    mm = torch.stack([minmax[..., 0].min(dim=0).values, minmax[..., 1].max(dim=0).values], dim=1)
+    return out_i, out_s, mm
+
+
+class ShardedIndex:
+    """One rank's handle on a row-sharded index (world size 1 degenerates to the local DenseIndex)."""
+
+    def __init__(self, local_index, group: Optional[dist.ProcessGroup] = None):
+        self.local = local_index
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def search_device(self, queries_bf16: torch.Tensor, k: int):
+        """Every rank passes the SAME query block; every rank returns the same global (ids, scores, minmax)."""
+        from .index import merge_topk
+        ids, scores, minmax = self.local.search_device(queries_bf16, k)
+        if self.world == 1:
+            return ids, scores, minmax
+        nq = queries_bf16.shape[0]
+        mine = pack_partial(ids, scores, minmax)
+        gathered = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        g_ids, g_scores, g_mm = unpack_partials(gathered, self.world, nq, k)
+        return merge_topk(g_scores, g_ids, g_mm)

@@ -1,0 +1,222 @@
+"""EmbeddingStore call surface on the B200 engine (reference: src/comorag/embedding_store.py).
+
+Same constructor, methods, attributes, return values, id scheme (namespace + "-" + md5(text),
+misc_utils.py:152-163) and parquet file (`vdb_<namespace>.parquet`, columns hash_id / content / embedding =
+large_string / large_string / list<float>) as the reference, so ComoRAG.py and its helpers use it unchanged.
+
+What is different underneath:
+  * rows live in one growing fp32 host matrix (not a Python list of N arrays) AND as bf16 rows of a
+    device-resident DenseIndex, filled straight from the encoder's device output;
+  * `search(queries, k)` runs the fused sm_100a top-k kernel over the shard instead of callers pulling the
+    whole matrix with get_embeddings() and doing np.dot + argsort per query (ComoRAG.py:937-967);
+  * parquet I/O goes through pyarrow arrays built from the matrix (no per-row Python objects).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import threading
+from copy import deepcopy
+from hashlib import md5
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+logger = logging.getLogger(__name__)
+
+
+def compute_mdhash_id(content: str, prefix: str = "") -> str:
+    """misc_utils.py:152-163."""
+    return prefix + md5(content.encode()).hexdigest()
+
+
+class _RowList:
+    """List-like, read-only view of the embedding matrix rows (`store.embeddings` in the reference is a
+    List[np.ndarray]; embedding_store.py:96,119)."""
+
+    def __init__(self, store: "EmbeddingStore"):
+        self._s = store
+
+    def __len__(self) -> int:
+        return self._s._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._s._host[j] for j in range(*i.indices(self._s._n))]
+        if i < 0:
+            i += self._s._n
+        if not 0 <= i < self._s._n:
+            raise IndexError("embedding index out of range")
+        return self._s._host[i]
+
+    def __iter__(self):
+        return (self._s._host[j] for j in range(self._s._n))
+
+
+class EmbeddingStore:
+    def __init__(self, embedding_model, db_filename, batch_size, namespace):
+        self.embedding_model = embedding_model
+        self.batch_size = batch_size
+        self.namespace = namespace
+        if not os.path.exists(db_filename):
+            logger.info(f"Creating working directory: {db_filename}")
+            os.makedirs(db_filename, exist_ok=True)
+        self.filename = os.path.join(db_filename, f"vdb_{self.namespace}.parquet")
+        self._lock = threading.RLock()
+        self._dim: Optional[int] = getattr(embedding_model, "embedding_dim", None)
+        self._host = np.zeros((0, self._dim or 0), dtype=np.float32)
+        self._n = 0
+        self._index = None  # DenseIndex, created on first use (needs a CUDA device)
+        self._index_rows = 0
+        self._load_data()
+
+    # ------------------------------------------------------------- bookkeeping
+    @property
+    def embeddings(self):
+        return _RowList(self)
+
+    def _rebuild_maps(self) -> None:
+        self.hash_id_to_idx = {h: i for i, h in enumerate(self.hash_ids)}
+        self.hash_id_to_row = {h: {"hash_id": h, "content": t} for h, t in zip(self.hash_ids, self.texts)}
+        self.hash_id_to_text = dict(zip(self.hash_ids, self.texts))
+        self.text_to_hash_id = {t: h for h, t in zip(self.hash_ids, self.texts)}
+
+    def _append_host(self, rows: np.ndarray) -> None:
+        rows = np.asarray(rows, dtype=np.float32)
+        if rows.ndim == 1:
+            rows = rows[None, :]
+        if self._dim is None or self._host.shape[1] == 0:
+            self._dim = rows.shape[1]
+            self._host = np.zeros((0, self._dim), dtype=np.float32)
+        n1 = self._n + rows.shape[0]
+        if n1 > self._host.shape[0]:
+            grown = np.empty((max(n1, int(self._host.shape[0] * 1.5) + 64), self._dim), dtype=np.float32)
+            grown[: self._n] = self._host[: self._n]
+            self._host = grown
+        self._host[self._n:n1] = rows
+        self._n = n1
+
+    # ------------------------------------------------------------------ inserts
+    def _nodes(self, texts: List[str]) -> Dict[str, Dict[str, str]]:
+        return {compute_mdhash_id(text, prefix=self.namespace + "-"): {"content": text} for text in texts}
+
+    def get_missing_string_hash_ids(self, texts: List[str]):
+        """embedding_store.py:44-61."""
+        nodes = self._nodes(texts)
+        if not nodes:
+            return {}
+        missing = [h for h in nodes if h not in self.hash_id_to_row]
+        return {h: {"hash_id": h, "content": nodes[h]["content"]} for h in missing}
+
+    def insert_strings(self, texts: List[str]):
+        """embedding_store.py:63-90: dedup by md5 id, encode what is missing, append, persist."""
+        with self._lock:
+            nodes = self._nodes(texts)
+            if not nodes:
+                return
+            missing_ids = [h for h in nodes if h not in self.hash_id_to_row]
+            logger.info(f"Inserting {len(missing_ids)} new records, {len(nodes) - len(missing_ids)} records already exist.")
+            if not missing_ids:
+                return {}
+            texts_to_encode = [nodes[h]["content"] for h in missing_ids]
+            missing_embeddings = self.embedding_model.batch_encode(texts_to_encode)
+            self._upsert(missing_ids, texts_to_encode, missing_embeddings)
+
+    def _upsert(self, hash_ids, texts, embeddings):
+        self._append_host(embeddings)
+        self.hash_ids.extend(hash_ids)
+        self.texts.extend(texts)
+        logger.info("Saving new records.")
+        self._save_data()
+
+    # -------------------------------------------------------------- persistence
+    def _load_data(self):
+        """embedding_store.py:92-107."""
+        if os.path.exists(self.filename):
+            import pyarrow.parquet as pq
+            table = pq.read_table(self.filename)
+            self.hash_ids = table.column("hash_id").to_pylist()
+            self.texts = table.column("content").to_pylist()
+            emb = table.column("embedding").combine_chunks()
+            n = len(self.hash_ids)
+            flat = emb.flatten().to_numpy(zero_copy_only=False).astype(np.float32, copy=False)
+            if n and flat.size % n != 0:
+                raise ValueError(f"{self.filename}: ragged embedding column")
+            self._host = np.zeros((0, 0), dtype=np.float32)
+            self._n = 0
+            if n:
+                self._dim = flat.size // n
+                self._append_host(flat.reshape(n, self._dim))
+            self._rebuild_maps()
+            assert len(self.hash_ids) == len(self.texts) == self._n
+            logger.info(f"Loaded {len(self.hash_ids)} records from {self.filename}")
+        else:
+            self.hash_ids, self.texts = [], []
+            self._rebuild_maps()  # the reference leaves hash_id_to_text / text_to_hash_id undefined here (:106-107)
+
+    def _save_data(self):
+        """embedding_store.py:109-120: whole-file rewrite, same schema (large_string, large_string, list<float>)."""
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+        n, d = self._n, (self._dim or 0)
+        values = pa.array(self._host[:n].reshape(-1), type=pa.float32())
+        offsets = pa.array(np.arange(0, (n + 1) * d, d, dtype=np.int32) if d else np.zeros(n + 1, np.int32), type=pa.int32())
+        table = pa.table({
+            "hash_id": pa.array(self.hash_ids, type=pa.large_string()),
+            "content": pa.array(self.texts, type=pa.large_string()),
+            "embedding": pa.ListArray.from_arrays(offsets, values),
+        })
+        tmp = self.filename + ".tmp"
+        pq.write_table(table, tmp)
+        os.replace(tmp, self.filename)
+        self._rebuild_maps()
+        logger.info(f"Saved {len(self.hash_ids)} records to {self.filename}")
+
+    # ------------------------------------------------------------------ lookups
+    def get_row(self, hash_id):
+        return self.hash_id_to_row[hash_id]
+
+    def get_rows(self, hash_ids, dtype=np.float32):
+        if not hash_ids:
+            return {}
+        return {id: self.hash_id_to_row[id] for id in hash_ids}
+
+    def get_all_ids(self):
+        return deepcopy(self.hash_ids)
+
+    def get_text_for_all_rows(self):
+        return deepcopy(self.hash_id_to_row)
+
+    def get_embedding(self, hash_id, dtype=np.float32) -> np.ndarray:
+        return self._host[self.hash_id_to_idx[hash_id]].astype(dtype)
+
+    def get_embeddings(self, hash_ids, dtype=np.float32):
+        if not hash_ids:
+            return []
+        indices = np.array([self.hash_id_to_idx[h] for h in hash_ids], dtype=np.intp)
+        return self._host[: self._n][indices].astype(dtype, copy=False)
+
+    def get_hash_id_to_order(self) -> Dict[str, int]:
+        return {h: idx for idx, h in enumerate(self.hash_ids)}
+
+    # ------------------------------------------------------------ engine extras
+    @property
+    def index(self):
+        """Device-resident bf16 shard holding every stored row (built / extended lazily)."""
+        from .index import DenseIndex
+        with self._lock:
+            if self._index is None:
+                if self._dim is None:
+                    raise ValueError("empty store: embedding width unknown")
+                device = getattr(self.embedding_model, "device", None)
+                self._index = DenseIndex(self._dim, device=device, capacity=max(self._n, 1024))
+                self._index_rows = 0
+            if self._index_rows < self._n:
+                self._index.add(self._host[self._index_rows: self._n])
+                self._index_rows = self._n
+            return self._index
+
+    def search(self, query_embeddings, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Top-k rows for a block of query embeddings [nq, D] (host or device): (row indices int64 [nq, k]
+        into hash_ids/texts, raw inner products [nq, k], (min, max) over all rows [nq, 2])."""
+        return self.index.search(query_embeddings, k)

@@ -1,0 +1,79 @@
+"""Retrieval math of ComoRAG.py / utils/embed_utils.py on the fused top-k kernel.
+
+Each function keeps the reference function's name, arguments and return convention; where the reference
+returns a FULL ranking of all N rows (dense_passage_retrieval feeds every rank into PPR,
+ComoRAG.py:1034-1042) an exact full-sort path is kept for small N and the top-k path is used for large N
+(the narrowing is documented in DESIGN.md).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from .index import DenseIndex, MAX_K
+
+
+def min_max_normalize(x: np.ndarray) -> np.ndarray:
+    """misc_utils.py:141-150."""
+    x = np.asarray(x)
+    min_val, max_val = np.min(x), np.max(x)
+    range_val = max_val - min_val
+    if range_val == 0:
+        return np.ones_like(x)
+    return (x - min_val) / range_val
+
+
+def normalize_topk_scores(scores: np.ndarray, minmax: np.ndarray) -> np.ndarray:
+    """Reproduce min_max_normalize(all N scores)[top-k ids] from the k survivors and the kernel's global
+    (min, max): (s - min) / (max - min), all ones if the range is 0 (misc_utils.py:141-150)."""
+    mn, mx = minmax[..., 0:1], minmax[..., 1:2]
+    rng = mx - mn
+    out = (scores - mn) / np.where(rng == 0, 1, rng)
+    return np.where(rng == 0, np.ones_like(scores), out).astype(np.float32)
+
+
+def dense_topk(index: DenseIndex, query_embeddings, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Batched dense_passage_retrieval truncated to the first k ranks: (ids int64 [nq, k], min-max-normalised
+    scores fp32 [nq, k]) -- what tri_retrieve consumes at ComoRAG.py:499,516 (first qa_*_top_k ids)."""
+    ids, scores, minmax = index.search(query_embeddings, min(k, MAX_K))
+    return ids, normalize_topk_scores(scores, minmax)
+
+
+def dense_passage_retrieval(index: DenseIndex, query_embedding, top_k: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """ComoRAG.py:950-967 for one query embedding [1, D] or [D].
+
+    top_k=None keeps the reference contract (a permutation of ALL rows + all normalised scores): scores for
+    every row are produced on the device in one pass and sorted there.  With top_k only the first top_k ranks
+    are produced by the fused kernel.
+    """
+    import torch
+    if top_k is not None:
+        ids, sc = dense_topk(index, query_embedding, top_k)
+        return ids[0], sc[0]
+    q = index.prepare_queries(query_embedding)
+    scores = (index.matrix().float() @ q[0, : index.dim].float())  # [N] fp32 on device
+    mn, mx = scores.min(), scores.max()
+    norm = torch.ones_like(scores) if float(mx - mn) == 0.0 else (scores - mn) / (mx - mn)
+    order = torch.argsort(norm, descending=True, stable=True)
+    return order.cpu().numpy(), norm[order].cpu().numpy()
+
+
+def get_fact_scores_topk(index: DenseIndex, query_embedding, link_top_k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """get_fact_scores + the argsort[-k:][::-1] pick that follows it (ComoRAG.py:937-948, :475, :1073)."""
+    ids, sc = dense_topk(index, query_embedding, link_top_k)
+    return ids[0], sc[0]
+
+
+def get_similar_summaries(query: str, level_store, embedding_model, top_k: int = 3,
+                          instruction: Optional[str] = None) -> Tuple[List[str], List[float]]:
+    """embed_utils.py:109-161 on an engine EmbeddingStore: no per-call matrix rebuild, fused top-k."""
+    level_ids = level_store.get_all_ids()
+    if not level_ids:
+        return [], []
+    query_embedding = embedding_model.batch_encode(
+        query, instruction='Given a question, retrieve relevant documents that best answer the question.', norm=True)
+    k = min(top_k, len(level_ids), MAX_K)
+    ids, scores, minmax = level_store.search(query_embedding, k)
+    norm = normalize_topk_scores(scores, minmax)[0]
+    return [level_store.texts[i] for i in ids[0] if i >= 0], [float(s) for s, i in zip(norm, ids[0]) if i >= 0]

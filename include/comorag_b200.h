@@ -87,6 +87,16 @@ CRAG_API int crag_search_topk(const void* corpus, int64_t n_rows, int dim, int64
                      const void* queries, int nq, int k, int64_t* out_ids, float* out_scores, float* out_minmax,
                      void* workspace, size_t workspace_bytes, crag_stream_t stream);
 
+/* The two halves of crag_search_topk for ONE pass (nq <= 32), exported so a caller can time or overlap them:
+ * crag_search_scan streams the shard once and leaves per-CTA partial lists in the workspace;
+ * crag_search_finalize merges them into (ids, scores, minmax).  Same argument rules as crag_search_topk. */
+CRAG_API int crag_search_scan(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride,
+                              const void* queries, int nq, int k, void* workspace, size_t workspace_bytes,
+                              crag_stream_t stream);
+CRAG_API int crag_search_finalize(const void* workspace, size_t workspace_bytes, int64_t n_rows, int nq, int k,
+                                  int64_t row_offset, int64_t* out_ids, float* out_scores, float* out_minmax,
+                                  crag_stream_t stream);
+
 /* Merge `parts` per-shard results (the all-gathered output of
  * crag_search_topk on every rank, rank-major) into the global top-k.
  *
