@@ -1,0 +1,55 @@
+"""The N>1 exchange step on CPU: world_size-2 gloo processes each hold a row shard, compute their local exact top-k
+with the oracle, all-gather the packed partials (the same payload ShardedIndex sends over NCCL) and merge; the result
+must equal the oracle's top-k over the unsharded corpus."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from comorag_b200.dist import merge_partials_reference, pack_partial, shard_bounds, unpack_partials
+from oracle import search_oracle as so
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _corpus(n, d):
+    g = torch.Generator().manual_seed(11)
+    E = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1).bfloat16().float().numpy()
+    Q = torch.nn.functional.normalize(torch.randn(6, d, generator=g), dim=1).bfloat16().float().numpy()
+    return E, Q
+
+
+def _worker(rank, world, port, n, d, k, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    E, Q = _corpus(n, d)
+    offs = shard_bounds(n, world)
+    ids, scores, mm, _ = so.topk_exact(E[offs[rank]:offs[rank + 1]], Q, k, row_offset=offs[rank])
+    mine = pack_partial(torch.from_numpy(ids), torch.from_numpy(scores.astype(np.float32)), torch.from_numpy(mm.astype(np.float32)))
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    g_ids, g_scores, g_mm = unpack_partials(torch.cat(gathered), world, Q.shape[0], k)
+    oi, os_, om = merge_partials_reference(g_ids, g_scores, g_mm, k)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), ids=oi.numpy(), scores=os_.numpy(), mm=om.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,k", [(3001, 10), (9, 10)])
+def test_two_rank_shard_merge_equals_global_topk(tmp_path, n, k):
+    d, world = 64, 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, d, k, str(tmp_path)), nprocs=world, join=True)
+    E, Q = _corpus(n, d)
+    want_i, want_s, want_mm, gaps = so.topk_exact(E, Q, k)
+    for r in range(world):
+        got = np.load(tmp_path / f"r{r}.npz")
+        so.assert_topk_matches(got["ids"], got["scores"].astype(np.float64), want_i, want_s, gaps, score_tol=1e-6)
+        np.testing.assert_allclose(got["mm"], want_mm, atol=1e-6)

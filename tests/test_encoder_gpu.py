@@ -1,0 +1,194 @@
+"""GPU parity of the encoder path: each kernel against a plain torch fp32 statement of the same op, the whole forward
+against the torch oracle, and the drop-in BGEEmbeddingModel / EmbeddingStore against embeddings the REFERENCE produced
+for the synthetic checkpoint (tests/golden/encoder_golden.npz)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoder_oracle as eo
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(__file__)
+CKPT = os.path.join(HERE, "golden", "bge-tiny-synth")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from comorag_b200 import _native
+    _native.load()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(HERE, "golden", "encoder_golden.npz"), allow_pickle=True)
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(128, 128, 64, 0), (300, 384, 384, 0), (1000, 1152, 384, 0), (777, 1536, 384, 1),
+                                       (512, 384, 1536, 2), (2048, 3072, 1024, 0), (2048, 1024, 4096, 2), (2048, 4096, 1024, 1),
+                                       (1, 768, 768, 0), (129, 8, 8, 0)])
+def test_gemm_epilogues(dev, M, N, K, epi):
+    from comorag_b200 import _native
+    lib = _native.load()
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(N, K, generator=g, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(N, generator=g, device=dev)
+    res = torch.randn(M, N, generator=g, device=dev).bfloat16()
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev)
+    rc = lib.crag_gemm_bf16(a.data_ptr(), K, w.data_ptr(), K, bias.data_ptr(), res.data_ptr(), N, out.data_ptr(), N, M, N, K,
+                            epi, torch.cuda.current_stream().cuda_stream)
+    _native.check(rc, "crag_gemm_bf16")
+    ref = a.float() @ w.float().T + bias
+    if epi == 1:
+        ref = torch.nn.functional.gelu(ref)
+    if epi == 2:
+        ref = ref + res.float()
+    err = (out.float() - ref).abs()
+    assert bool((err <= 0.01 * ref.abs() + 0.02).all()), float(err.max())   # bf16 output rounding
+
+
+@pytest.mark.parametrize("H,heads,lens", [(128, 4, [5, 64, 65, 1, 130]), (1024, 16, [512, 33, 200]), (384, 12, [77, 512]),
+                                          (768, 12, [128] * 3)])
+def test_varlen_attention(dev, H, heads, lens):
+    from comorag_b200 import _native
+    lib = _native.load()
+    dh, T = H // heads, sum(lens)
+    g = torch.Generator(device=dev).manual_seed(H)
+    qkv = torch.randn(T, 3 * H, generator=g, device=dev).bfloat16()
+    cu = torch.tensor([0] + np.cumsum(lens).tolist(), dtype=torch.int32, device=dev)
+    ctx = torch.full((T, H), float("nan"), dtype=torch.bfloat16, device=dev)
+    rc = lib.crag_attention_varlen(qkv.data_ptr(), cu.data_ptr(), len(lens), max(lens), H, heads, ctx.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream)
+    _native.check(rc, "crag_attention_varlen")
+    ref, s = torch.zeros(T, H, device=dev), 0
+    for L in lens:
+        x = qkv[s:s + L].float()
+        q, k, v = (x[:, j * H:(j + 1) * H].view(L, heads, dh).transpose(0, 1) for j in range(3))
+        ref[s:s + L] = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), -1) @ v).transpose(0, 1).reshape(L, H)
+        s += L
+    assert float((ctx.float() - ref).abs().max()) < 0.03
+
+
+@pytest.mark.parametrize("H", [128, 384, 768, 1024])
+def test_layernorm(dev, H):
+    from comorag_b200 import _native
+    lib = _native.load()
+    g = torch.Generator(device=dev).manual_seed(H)
+    x = (torch.randn(1001, H, generator=g, device=dev) * 3 + 1).bfloat16()
+    gam, bet = torch.randn(H, generator=g, device=dev), torch.randn(H, generator=g, device=dev)
+    out = torch.zeros_like(x)
+    _native.check(lib.crag_layernorm(x.data_ptr(), 1001, H, gam.data_ptr(), bet.data_ptr(), 1e-12, out.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream), "crag_layernorm")
+    ref = torch.nn.functional.layer_norm(x.float(), (H,), gam, bet, 1e-12)
+    assert bool(((out.float() - ref).abs() <= 0.01 * ref.abs() + 0.01).all())
+
+
+def test_pool_normalize_matches_reference_pooling(dev):
+    from comorag_b200 import _native
+    lib = _native.load()
+    H, lens = 384, [3, 512, 77, 1]
+    g = torch.Generator(device=dev).manual_seed(1)
+    hid = torch.randn(sum(lens), H, generator=g, device=dev).bfloat16()
+    cu = torch.tensor([0] + np.cumsum(lens).tolist(), dtype=torch.int32, device=dev)
+    out = torch.zeros(len(lens), H, device=dev)
+    shard = torch.zeros(len(lens), 512, dtype=torch.bfloat16, device=dev)      # bf16 rows with a wider stride
+    _native.check(lib.crag_pool_normalize(hid.data_ptr(), cu.data_ptr(), len(lens), H, 1, out.data_ptr(), shard.data_ptr(), 512,
+                                          torch.cuda.current_stream().cuda_stream), "crag_pool_normalize")
+    L = max(lens)
+    padded, mask, s = torch.zeros(len(lens), L, H, device=dev), torch.zeros(len(lens), L, device=dev), 0
+    for i, n in enumerate(lens):
+        padded[i, :n], mask[i, :n] = hid[s:s + n].float(), 1
+        s += n
+    ref = torch.nn.functional.normalize(eo.mean_pooling(padded, mask), p=2, dim=1)
+    assert float((out - ref).abs().max()) < 1e-5
+    assert float((shard[:, :H].float() - ref).abs().max()) < 4e-3 and float(shard[:, H:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cargs,lens,std", [((128, 2, 4, 256, 1000), [5, 64, 65, 1, 130, 17], 0.08),
+                                            ((384, 4, 12, 1536, 30522), [512, 100, 37], 0.02),
+                                            ((1024, 24, 16, 4096, 30522), [512, 128, 45], 0.02)])
+def test_forward_vs_torch_oracle(dev, cargs, lens, std):
+    """cosine >= 0.999 and max-abs <= 1e-2 per embedding vs the fp32 oracle on the same bf16-rounded weights
+    (SURVEY.md section 8d); the bge-large shape is BASELINE config 2/3's encoder."""
+    from comorag_b200.encoder import BertEncoderB200, EncoderConfig, random_state_dict
+    cfg = EncoderConfig(*cargs)
+    sd = random_state_dict(cfg, seed=1, std=std, device=dev)
+    enc = BertEncoderB200(cfg, sd, dev)
+    g = torch.Generator().manual_seed(7)
+    seqs = [([101] + torch.randint(5, cfg.vocab_size, (L - 2,), generator=g).tolist() + [102]) if L >= 2 else [101] for L in lens]
+    out = enc.encode_token_lists(seqs)
+    sd_q = {k: (v.bfloat16().float() if v.dim() == 2 else v) for k, v in sd.items()}
+    ref = eo.encode_token_lists(sd_q, cfg, seqs)
+    assert float(torch.nn.functional.cosine_similarity(out, ref, dim=1).min()) > 0.999
+    assert float((out - ref).abs().max()) < 1e-2
+    # rows do not depend on what they are batched with (unpadded packing == padding + mask)
+    alone = enc.encode_token_lists(seqs[:1])
+    assert float((alone[0] - out[0]).abs().max()) < 1e-6
+
+
+def test_dropin_model_matches_reference_embeddings(dev, gold):
+    """BGEEmbeddingModel (ours) on the synthetic checkpoint vs what the REFERENCE's BGEEmbeddingModel returned."""
+    from comorag_b200.config import EngineConfig
+    from comorag_b200.embedding_model import BGEEmbeddingModel, _get_embedding_model_class
+    assert _get_embedding_model_class(CKPT) is BGEEmbeddingModel
+    cfg = EngineConfig(embedding_model_name=CKPT, embedding_batch_size=4, embedding_max_seq_len=512)
+    model = BGEEmbeddingModel(global_config=cfg, embedding_model_name=CKPT)
+    texts = gold["texts"].tolist()
+    assert model.embedding_dim == 128
+    ids = model._tokenize(["Generate a representation for this sentence to retrieve relevant articles:" + t for t in texts], 512)
+    assert [list(x) for x in ids] == [t.tolist() for t in gold["token_ids"]]      # same tokenizer call as the reference
+    emb = model.batch_encode(texts)
+    assert emb.dtype == np.float32 and emb.shape == gold["emb_batch"].shape and emb.flags["C_CONTIGUOUS"]
+    ref = gold["emb_batch"]
+    cos = (emb * ref).sum(1) / (np.linalg.norm(emb, axis=1) * np.linalg.norm(ref, axis=1))
+    assert cos.min() > 0.999 and np.abs(emb - ref).max() < 1e-2
+    # centred comparison: random-weight encoders put every text near one direction; remove it so the check bites
+    c_emb, c_ref = emb - ref.mean(0), ref - ref.mean(0)
+    ccos = (c_emb * c_ref).sum(1) / (np.linalg.norm(c_emb, axis=1) * np.linalg.norm(c_ref, axis=1))
+    assert ccos.min() > 0.99, ccos
+    n_c, n_q = int(gold["n_chunks"]), int(gold["n_questions"])
+    one = model.batch_encode(texts[n_c], instruction="ignored", norm=True)      # str input -> [1, D]; kwargs ignored
+    assert one.shape == (1, 128) and np.abs(one[0] - emb[n_c]).max() < 1e-5
+    np.testing.assert_allclose(model.encode_queries(texts[n_c:n_c + n_q]), emb[n_c:n_c + n_q], atol=1e-5)
+    t = model.encode(texts[:3])                                                  # positional surface, torch.Tensor, no prefix
+    assert isinstance(t, torch.Tensor) and np.abs(t.cpu().numpy() - gold["emb_encode"]).max() < 1e-2
+    np.testing.assert_allclose(model.get_query_doc_scores(emb[:1], emb), emb[:1] @ emb.T)
+
+
+def test_cinderella_plumbing_top10_matches_reference_math(dev, gold, tmp_path):
+    """BASELINE config 1: chunks -> EmbeddingStore.insert_strings -> device index -> top-k; ids equal the reference's
+    np.dot + argsort on the reference's own embeddings wherever its score gaps exceed the bf16 storage noise."""
+    from comorag_b200.config import EngineConfig
+    from comorag_b200.embedding_model import BGEEmbeddingModel
+    from comorag_b200.embedding_store import EmbeddingStore
+    from oracle import search_oracle as so
+    cfg = EngineConfig(embedding_model_name=CKPT, embedding_batch_size=4, embedding_max_seq_len=512)
+    model = BGEEmbeddingModel(global_config=cfg, embedding_model_name=CKPT)
+    texts = gold["texts"].tolist()
+    n_c, n_q = int(gold["n_chunks"]), int(gold["n_questions"])
+    store = EmbeddingStore(model, str(tmp_path / "chunk_embeddings"), 4, "chunk")
+    store.insert_strings(texts[:n_c] + texts[n_c + n_q:])
+    assert store.insert_strings(texts[:2]) == {}
+    ref_rows = np.concatenate([gold["emb_batch"][:n_c], gold["emb_batch"][n_c + n_q:]])
+    got_rows = store.get_embeddings(store.get_all_ids())
+    assert np.abs(got_rows - ref_rows).max() < 1e-2
+    q_emb = model.batch_encode(texts[n_c:n_c + n_q])
+    ids, scores, minmax = store.search(q_emb, min(10, len(store.hash_ids)))
+    k = ids.shape[1]
+    for qi in range(n_q):
+        ref_ids, ref_sc = so.dense_passage_retrieval(ref_rows, gold["emb_batch"][n_c + qi][None])
+        raw = np.dot(ref_rows, gold["emb_batch"][n_c + qi])
+        order = np.argsort(-raw)
+        gaps = -np.diff(raw[order])
+        # ranks separated by more than the bf16/encoder noise (1e-2 abs on unit vectors -> ~2e-2 on a dot) must agree
+        j = 0
+        while j < k - 1 and gaps[j] > 4e-2:
+            assert ids[qi, j] == order[j]
+            j += 1
+        assert set(ids[qi].tolist()) <= set(range(len(store.hash_ids)))
+        assert np.abs(np.sort(scores[qi]) - np.sort(raw[ids[qi]])).max() < 3e-2

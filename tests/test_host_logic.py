@@ -1,0 +1,62 @@
+"""Host-side logic that needs no GPU: config bag, factory dispatch, score normalisation, shard bounds, packing."""
+import numpy as np
+import pytest
+import torch
+
+from comorag_b200.dist import merge_partials_reference, pack_partial, shard_bounds, unpack_partials
+from comorag_b200.retrieval import min_max_normalize, normalize_topk_scores
+from oracle import search_oracle as so
+
+
+def test_embedding_config_bag():
+    from comorag_b200.embedding_model.base import EmbeddingConfig
+    c = EmbeddingConfig.from_dict({"norm": True, "encode_params": {"max_length": 512}})
+    assert c.norm is True and c["encode_params"]["max_length"] == 512 and "norm" in c
+    c.extra = 3
+    assert c.to_dict()["extra"] == 3
+    with pytest.raises(AttributeError):
+        c.missing
+    with pytest.raises(KeyError):
+        c["missing"]
+    del c["extra"]
+    assert "extra" not in c
+
+
+def test_normalize_topk_scores_reproduces_min_max_of_all_scores():
+    rng = np.random.default_rng(0)
+    all_scores = rng.standard_normal((3, 1000)).astype(np.float32)
+    top = np.argsort(-all_scores, axis=1)[:, :10]
+    raw = np.take_along_axis(all_scores, top, axis=1)
+    minmax = np.stack([all_scores.min(1), all_scores.max(1)], 1)
+    want = np.stack([so.min_max_normalize(all_scores[i])[top[i]] for i in range(3)])
+    np.testing.assert_allclose(normalize_topk_scores(raw, minmax), want, atol=1e-6)
+    # zero range -> all ones, as the reference (misc_utils.py:147-148)
+    np.testing.assert_array_equal(normalize_topk_scores(np.full((1, 4), 0.5, np.float32), np.array([[0.5, 0.5]], np.float32)),
+                                  np.ones((1, 4), np.float32))
+    np.testing.assert_array_equal(min_max_normalize(np.array([2.0, 2.0])), np.ones(2))
+
+
+def test_shard_bounds_cover_rows_exactly():
+    for n, w in [(10_000_000, 8), (7, 3), (5, 8), (0, 2), (1024, 1)]:
+        o = shard_bounds(n, w)
+        assert o[0] == 0 and o[-1] == n and len(o) == w + 1
+        sizes = [o[i + 1] - o[i] for i in range(w)]
+        assert max(sizes) - min(sizes) <= 1 and sorted(sizes, reverse=True) == sizes
+
+
+def test_pack_unpack_roundtrip_and_merge_rule():
+    g = torch.Generator().manual_seed(0)
+    world, nq, k = 3, 5, 4
+    scores = torch.randn(world, nq, k, generator=g).sort(dim=2, descending=True).values
+    ids = torch.arange(world * nq * k).view(world, nq, k)
+    ids[2, :, 3] = -1
+    scores[2, :, 3] = float("-inf")
+    mm = torch.randn(world, nq, 2, generator=g)
+    buf = torch.cat([pack_partial(ids[r], scores[r], mm[r]) for r in range(world)])
+    i2, s2, m2 = unpack_partials(buf, world, nq, k)
+    assert torch.equal(i2, ids) and torch.equal(s2, scores) and torch.equal(m2, mm)
+    oi, os_, om = merge_partials_reference(ids, scores, mm, k)
+    flat_s = scores.permute(1, 0, 2).reshape(nq, -1)
+    assert torch.equal(os_, flat_s.sort(dim=1, descending=True).values[:, :k])
+    assert torch.equal(om[:, 0], mm[..., 0].min(0).values) and torch.equal(om[:, 1], mm[..., 1].max(0).values)
+    assert (oi >= 0).all()

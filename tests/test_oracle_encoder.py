@@ -1,0 +1,53 @@
+"""The torch-fp32 encoder oracle reproduces the embeddings the reference's BGEEmbeddingModel produced (through HF
+BertModel) for the synthetic checkpoint: tests/golden/encoder_golden.npz, made by make_golden_encoder.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from comorag_b200.encoder import EncoderConfig
+from oracle import encoder_oracle as eo
+
+HERE = os.path.dirname(__file__)
+CKPT = os.path.join(HERE, "golden", "bge-tiny-synth")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(HERE, "golden", "encoder_golden.npz"), allow_pickle=True)
+
+
+@pytest.fixture(scope="module")
+def model():
+    from safetensors.torch import load_file
+    return EncoderConfig.from_hf_json(os.path.join(CKPT, "config.json")), load_file(os.path.join(CKPT, "model.safetensors"))
+
+
+def test_batch_encode_embeddings_match_reference(gold, model):
+    cfg, sd = model
+    seqs = [t.tolist() for t in gold["token_ids"]]
+    emb = eo.encode_token_lists(sd, cfg, seqs, batch_size=4).numpy()   # the golden run used embedding_batch_size=4
+    np.testing.assert_allclose(emb, gold["emb_batch"], rtol=0, atol=2e-6)
+    assert np.allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-5)
+
+
+def test_positional_encode_has_no_instruction_prefix(gold, model):
+    cfg, sd = model
+    seqs = [t.tolist() for t in gold["token_ids_plain"]]
+    emb = eo.encode_token_lists(sd, cfg, seqs).numpy()
+    np.testing.assert_allclose(emb, gold["emb_encode"], rtol=0, atol=2e-6)
+
+
+def test_reference_ignores_the_instruction_kwarg(gold):
+    """batch_encode(q, instruction=...) and encode_queries(q) equal the passage-instruction rows."""
+    n_c, n_q = int(gold["n_chunks"]), int(gold["n_questions"])
+    np.testing.assert_allclose(gold["emb_query"], gold["emb_batch"][n_c:n_c + n_q], atol=1e-6)
+    np.testing.assert_allclose(gold["emb_encode_queries"], gold["emb_batch"][n_c:n_c + n_q], atol=1e-6)
+
+
+def test_padding_does_not_change_a_row(model):
+    cfg, sd = model
+    a = eo.encode_token_lists(sd, cfg, [[2, 10, 11, 12, 3]])
+    b = eo.encode_token_lists(sd, cfg, [[2, 10, 11, 12, 3], [2] + list(range(5, 200)) + [3]])
+    assert torch.allclose(a[0], b[0], atol=1e-6)

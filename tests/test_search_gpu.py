@@ -1,0 +1,190 @@
+"""GPU parity of the fused search kernel (through the C ABI / host classes) against the numpy oracle, the reference's
+own golden outputs, and size-independent properties at BASELINE scale."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import search_oracle as so
+from util_search import make_unit_rows, torch_reference_topk
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "search_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from comorag_b200 import _native
+    _native.load()  # fail loudly if the CUDA extension is missing
+    return torch.device("cuda:0")
+
+
+def _index(corpus_bf16, dev, row_offset=0):
+    from comorag_b200.index import DenseIndex
+    return DenseIndex.from_tensor(corpus_bf16.to(dev).contiguous(), row_offset=row_offset)
+
+
+CASES = [  # n_rows, dim, nq, k
+    (128, 64, 32, 10), (1000, 64, 1, 5), (100, 128, 3, 10), (7, 64, 2, 10), (1, 64, 1, 1), (129, 64, 33, 64),
+    (5000, 384, 7, 50), (20000, 768, 40, 100), (30000, 1024, 32, 10), (4097, 256, 5, 128),
+]
+
+
+@pytest.mark.parametrize("n,dim,nq,k", CASES)
+def test_topk_ids_bit_exact_vs_numpy_oracle(dev, n, dim, nq, k):
+    corpus, queries = make_unit_rows(n, dim, 100 + n), make_unit_rows(nq, dim, 200 + n)
+    want_i, want_s, want_mm, gaps = so.topk_exact(corpus.float().numpy(), queries.float().numpy(), k)
+    ids, scores, minmax = _index(corpus, dev).search(queries.float().numpy(), k)
+    so.assert_topk_matches(ids, scores.astype(np.float64), want_i, want_s, gaps, score_tol=1e-3)
+    np.testing.assert_allclose(minmax, want_mm, atol=1e-5)
+
+
+def test_exact_ties_resolve_to_ascending_row_id(dev):
+    base = make_unit_rows(1500, 128, 7)
+    corpus = torch.cat([base, base])            # every score appears twice
+    queries = make_unit_rows(9, 128, 8)
+    ids, scores, _ = _index(corpus, dev).search(queries.float().numpy(), 10)
+    assert (ids[:, 0::2] + 1500 == ids[:, 1::2]).all() and (scores[:, 0::2] == scores[:, 1::2]).all()
+    want_i, want_s, _, gaps = so.topk_exact(corpus.float().numpy(), queries.float().numpy(), 10)
+    np.testing.assert_array_equal(ids, want_i)
+
+
+def test_constant_corpus_and_zero_range(dev):
+    corpus = make_unit_rows(1, 64, 3).repeat(300, 1)
+    q = make_unit_rows(2, 64, 4)
+    ids, scores, minmax = _index(corpus, dev).search(q.float().numpy(), 5)
+    np.testing.assert_array_equal(ids, np.tile(np.arange(5), (2, 1)))
+    assert (minmax[:, 0] == minmax[:, 1]).all()
+    from comorag_b200.retrieval import normalize_topk_scores
+    np.testing.assert_array_equal(normalize_topk_scores(scores, minmax), np.ones((2, 5), np.float32))
+
+
+def test_empty_shard_and_row_offset(dev):
+    from comorag_b200.index import DenseIndex
+    empty = DenseIndex(64, device=dev)
+    ids, scores, minmax = empty.search(make_unit_rows(3, 64, 1).float().numpy(), 4)
+    assert (ids == -1).all() and np.isneginf(scores).all() and np.isposinf(minmax[:, 0]).all() and np.isneginf(minmax[:, 1]).all()
+    corpus = make_unit_rows(500, 64, 2)
+    a, sa, _ = _index(corpus, dev).search(make_unit_rows(3, 64, 1).float().numpy(), 4)
+    b, sb, _ = _index(corpus, dev, row_offset=10_000_000_000).search(make_unit_rows(3, 64, 1).float().numpy(), 4)
+    np.testing.assert_array_equal(a + 10_000_000_000, b)
+    np.testing.assert_array_equal(sa, sb)
+
+
+def test_unaligned_dim_is_zero_padded(dev):
+    from comorag_b200.index import DenseIndex
+    corpus, queries = make_unit_rows(700, 100, 5), make_unit_rows(4, 100, 6)   # 100 -> padded to 128
+    idx = DenseIndex(100, device=dev)
+    idx.add(corpus.float().numpy()[:300])
+    idx.add(corpus[300:])
+    ids, scores, _ = idx.search(queries.float().numpy(), 10)
+    want_i, want_s, _, gaps = so.topk_exact(corpus.float().numpy(), queries.float().numpy(), 10)
+    so.assert_topk_matches(ids, scores.astype(np.float64), want_i, want_s, gaps)
+
+
+def test_argument_errors_are_reported_not_swallowed(dev):
+    from comorag_b200 import _native
+    from comorag_b200.index import DenseIndex
+    idx = DenseIndex(64, device=dev)
+    idx.add(make_unit_rows(10, 64, 1))
+    with pytest.raises(ValueError):
+        idx.search_device(torch.zeros(2, 64, device=dev), 5)            # wrong dtype
+    with pytest.raises(ValueError):
+        idx.search(np.zeros((2, 64), np.float32), 0)
+    lib = _native.load()
+    rc = lib.crag_search_topk(0, 10, 72, 72, 0, 0, 1, 5, 0, 0, 0, 0, 0, 0)
+    assert rc < 0 and b"dim" in lib.crag_last_error()
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_reference_golden_rankings(dev, tag):
+    """Same top-50 ids and min-max-normalised scores as the reference's dense_passage_retrieval / top-5 facts."""
+    from comorag_b200.retrieval import dense_topk, get_fact_scores_topk
+    gold = np.load(GOLD)
+    n, d, seed = (int(x) for x in gold[f"dpr_{tag}_shape"])
+    g = torch.Generator().manual_seed(seed)
+    E = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1).bfloat16()
+    Q = gold[f"dpr_{tag}_Q"]
+    idx = _index(E, dev)
+    ids, norm_scores = dense_topk(idx, Q, 50)
+    _, _, _, gaps = so.topk_exact(E.float().numpy(), Q, 50)
+    so.assert_topk_matches(ids, norm_scores.astype(np.float64), gold[f"dpr_{tag}_ids"][:, :50],
+                           gold[f"dpr_{tag}_scores"][:, :50].astype(np.float64), gaps, score_tol=1e-3)
+    for qi in range(Q.shape[0]):
+        f_ids, _ = get_fact_scores_topk(idx, Q[qi:qi + 1], 5)
+        if gaps[qi, :5].min() > 2e-6:
+            np.testing.assert_array_equal(f_ids, gold[f"dpr_{tag}_fact_top5"][qi])
+    # full-ranking contract (ComoRAG.py:965): a permutation of all rows whose head is the golden head
+    from comorag_b200.retrieval import dense_passage_retrieval
+    order, sc = dense_passage_retrieval(idx, Q[0:1])
+    assert sorted(order.tolist()) == list(range(n)) and np.all(np.diff(sc) <= 0)
+    if gaps[0, :20].min() > 1e-5:
+        np.testing.assert_array_equal(order[:20], gold[f"dpr_{tag}_ids"][0, :20])
+
+
+def test_similar_summaries_golden(dev, tmp_path):
+    """get_similar_summaries on an engine store returns the reference's texts/scores (embed_utils.py:109-161)."""
+    from comorag_b200.embedding_store import EmbeddingStore
+    from comorag_b200.retrieval import get_similar_summaries
+    gold = np.load(GOLD)
+    E, q = gold["gss_E"], gold["gss_q"]
+
+    class M:
+        embedding_dim = E.shape[1]
+        device = dev
+
+        def batch_encode(self, texts, **kw):
+            if isinstance(texts, str):
+                return q
+            return np.stack([E[int(t.split()[1])] for t in texts])
+
+    store = EmbeddingStore(M(), str(tmp_path / "level_0"), 8, "level_0")
+    store.insert_strings([f"summary {i}" for i in range(E.shape[0])])
+    texts, scores = get_similar_summaries("query", store, M(), top_k=50)
+    assert [int(t.split()[1]) for t in texts] == gold["gss_idx"].tolist()
+    np.testing.assert_allclose(scores, gold["gss_scores"], atol=1e-3)
+
+
+def test_merge_kernel_matches_merge_rule(dev):
+    from comorag_b200.dist import merge_partials_reference
+    from comorag_b200.index import merge_topk
+    g = torch.Generator().manual_seed(0)
+    for world, nq, k in [(2, 5, 10), (8, 32, 10), (8, 3, 100), (1, 4, 7)]:
+        scores = torch.randn(world, nq, k, generator=g).sort(dim=2, descending=True).values
+        ids = torch.randint(0, 1 << 40, (world, nq, k), generator=g)
+        scores[-1, :, -1] = float("-inf")
+        ids[-1, :, -1] = -1
+        scores[0, 0, 1] = scores[0, 0, 0]                  # a tie inside one part
+        if world > 1:
+            scores[1, 0, 0] = scores[0, 0, 0]              # and across parts
+        mm = torch.randn(world, nq, 2, generator=g)
+        oi, os_, om = merge_topk(scores.to(dev), ids.to(dev), mm.to(dev))
+        wi, ws, wm = merge_partials_reference(ids, scores, mm, k)
+        assert torch.equal(oi.cpu(), wi) and torch.equal(os_.cpu(), ws) and torch.equal(om.cpu(), wm)
+
+
+def test_sharded_equals_unsharded_at_config2_scale(dev):
+    """1M x 1024 (BASELINE config 2): properties that do not need a CPU pass over the corpus -- descending scores,
+    valid distinct ids, returned scores equal recomputed dots, min/max bound every score, and searching 4 row shards
+    + merge gives bit-identical ids to searching the whole matrix."""
+    from comorag_b200.index import DenseIndex, merge_topk
+    n, dim, nq, k = 1_000_000, 1024, 32, 10
+    corpus = make_unit_rows(n, dim, 1234, device=dev)
+    queries = make_unit_rows(nq, dim, 4321, device=dev)
+    whole = DenseIndex.from_tensor(corpus)
+    ids, scores, mm = whole.search_device(queries, k)
+    assert (scores[:, :-1] >= scores[:, 1:]).all()
+    assert ((ids >= 0) & (ids < n)).all() and all(len(set(r.tolist())) == k for r in ids)
+    redo = (corpus[ids.view(-1)].float().view(nq, k, dim) * queries.float()[:, None, :]).sum(-1)
+    assert (redo - scores).abs().max() < 1e-4
+    assert (mm[:, 1] >= scores[:, 0] - 1e-6).all() and (mm[:, 0] <= scores[:, -1]).all()
+    bounds = [0, 250_000, 500_001, 750_130, n]
+    parts = [DenseIndex.from_tensor(corpus[bounds[i]:bounds[i + 1]], row_offset=bounds[i]).search_device(queries, k) for i in range(4)]
+    m_ids, m_scores, m_mm = merge_topk(torch.stack([p[1] for p in parts]), torch.stack([p[0] for p in parts]),
+                                       torch.stack([p[2] for p in parts]))
+    assert torch.equal(m_ids, ids) and torch.equal(m_scores, scores) and torch.equal(m_mm, mm)
+    want_i, want_s, want_mm, gaps = torch_reference_topk(corpus, queries, k)
+    so.assert_topk_matches(ids.cpu().numpy(), scores.double().cpu().numpy(), want_i, want_s, gaps)
+    np.testing.assert_allclose(mm.cpu().numpy(), want_mm, atol=1e-5)

@@ -1,0 +1,92 @@
+"""EmbeddingStore host logic against the reference's own behaviour (tests/golden/store_golden.json, produced by the
+reference's EmbeddingStore on the cinderella chunks).  A fake embedding model replays the reference's embeddings, so
+no GPU is touched: ids, dedup, return values, lookups, parquet schema and reload are what is checked."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from comorag_b200.embedding_store import EmbeddingStore, compute_mdhash_id
+
+HERE = os.path.dirname(__file__)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = json.load(open(os.path.join(HERE, "golden", "store_golden.json")))
+    g["embeddings"] = np.load(os.path.join(HERE, "golden", "store_golden_embeddings.npy"))
+    return g
+
+
+class ReplayModel:
+    """batch_encode returns the row the reference stored for that text."""
+
+    def __init__(self, gold):
+        self.table = dict(zip(gold["texts"], gold["embeddings"]))
+        self.embedding_dim = gold["embeddings"].shape[1]
+        self.calls = []
+
+    def batch_encode(self, texts, **kw):
+        self.calls.append(list(texts))
+        return np.stack([self.table[t] for t in texts]).astype(np.float32)
+
+
+def test_insert_lookup_and_parquet_match_reference(gold, tmp_path):
+    model = ReplayModel(gold)
+    chunks = gold["texts"][:6]
+    store = EmbeddingStore(model, str(tmp_path / "chunk_embeddings"), 4, "chunk")
+    assert os.path.basename(store.filename) == gold["filename"]
+    assert store.hash_ids == [] and store.hash_id_to_text == {} and store.text_to_hash_id == {}
+    r1 = store.insert_strings(chunks)
+    r2 = store.insert_strings(chunks[:2] + ["a brand new chunk"])
+    r3 = store.insert_strings(chunks[:2])
+    assert [repr(r1), repr(r2), repr(r3)] == gold["insert_returns"]
+    assert model.calls == [chunks, ["a brand new chunk"]]          # only missing texts are encoded
+    assert store.get_all_ids() == gold["hash_ids"]
+    assert store.texts == gold["texts"]
+    assert store.get_row(store.hash_ids[0]) == gold["row0"]
+    assert store.get_hash_id_to_order() == gold["hash_id_to_order"]
+    assert store.get_missing_string_hash_ids([chunks[0], "never seen"]) == gold["missing"]
+    assert store.get_missing_string_hash_ids([]) == {} and store.insert_strings([]) is None
+    e = store.get_embeddings(store.hash_ids[:3])
+    assert list(e.shape) == gold["get_embeddings_shape"] and str(e.dtype) == gold["get_embeddings_dtype"]
+    np.testing.assert_allclose(store.get_embedding(store.hash_ids[0])[:8], gold["embedding_row0_first8"], atol=1e-7)
+    assert store.get_embeddings([]) == [] and store.get_rows([]) == {}
+    assert len(store.embeddings) == 7 and store.embeddings[0].dtype == np.float32
+    with pytest.raises(KeyError):
+        store.get_row("chunk-doesnotexist")
+    import pyarrow.parquet as pq
+    schema = pq.read_schema(store.filename)
+    assert {n: str(schema.field(n).type) for n in schema.names} == gold["parquet_schema"]
+    # reload (checkpoint/resume path, embedding_store.py:92-107)
+    again = EmbeddingStore(model, str(tmp_path / "chunk_embeddings"), 4, "chunk")
+    assert again.get_all_ids() == gold["reloaded_hash_ids"]
+    np.testing.assert_array_equal(again.get_embeddings(again.hash_ids), store.get_embeddings(store.hash_ids))
+    assert again.text_to_hash_id[chunks[1]] == gold["hash_ids"][1]
+
+
+def test_reference_written_parquet_is_readable(gold, tmp_path):
+    """A parquet file in the reference's own layout (pandas: list<float> of per-row arrays) loads into the engine store."""
+    import pandas as pd
+    d = tmp_path / "s"
+    d.mkdir()
+    pd.DataFrame({"hash_id": gold["hash_ids"], "content": gold["texts"],
+                  "embedding": [r for r in gold["embeddings"]]}).to_parquet(d / "vdb_chunk.parquet", index=False)
+    store = EmbeddingStore(ReplayModel(gold), str(d), 4, "chunk")
+    assert store.get_all_ids() == gold["hash_ids"]
+    np.testing.assert_array_equal(store.get_embeddings(store.hash_ids), gold["embeddings"])
+
+
+def test_id_scheme_and_in_call_dedup(tmp_path):
+    assert compute_mdhash_id("abc", prefix="ns-") == "ns-900150983cd24fb0d6963f7d28e17f72"
+
+    class M:
+        embedding_dim = 4
+
+        def batch_encode(self, texts, **kw):
+            return np.arange(len(texts) * 4, dtype=np.float32).reshape(len(texts), 4)
+
+    s = EmbeddingStore(M(), str(tmp_path / "x"), 2, "entity")
+    s.insert_strings(["a", "b", "a"])          # duplicate inside one call collapses (dict keyed by id)
+    assert s.texts == ["a", "b"] and len(s.embeddings) == 2
