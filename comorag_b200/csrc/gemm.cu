@@ -37,6 +37,54 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+
+// bias (+GELU | +residual) on 32 consecutive fp32 accumulator columns of one output row, bf16 16-byte stores
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row, int col0, int M, int N,
+                                               const float* __restrict__ bias,
+                                               const __nv_bfloat16* __restrict__ residual, int64_t ldr,
+                                               __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  if (row >= M || col0 >= N) return;
+  __nv_bfloat16* orow = out + int64_t(row) * ldo + col0;
+  const __nv_bfloat16* rrow = (EPI == GEMM_EPI_BIAS_RESIDUAL) ? residual + int64_t(row) * ldr + col0 : nullptr;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {  // 8 columns (16 bytes) per store
+    if (col0 + v * 8 < N) {
+      float x[8];
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + v * 8 + 4));
+      x[0] = __uint_as_float(r[v * 8 + 0]) + b0.x;
+      x[1] = __uint_as_float(r[v * 8 + 1]) + b0.y;
+      x[2] = __uint_as_float(r[v * 8 + 2]) + b0.z;
+      x[3] = __uint_as_float(r[v * 8 + 3]) + b0.w;
+      x[4] = __uint_as_float(r[v * 8 + 4]) + b1.x;
+      x[5] = __uint_as_float(r[v * 8 + 5]) + b1.y;
+      x[6] = __uint_as_float(r[v * 8 + 6]) + b1.z;
+      x[7] = __uint_as_float(r[v * 8 + 7]) + b1.w;
+      if (EPI == GEMM_EPI_BIAS_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+      }
+      if (EPI == GEMM_EPI_BIAS_RESIDUAL) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(rrow + v * 8);
+        const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+          x[2 * j] += __bfloat162float(p.x);
+          x[2 * j + 1] += __bfloat162float(p.y);
+        }
+      }
+      uint4 o;
+      o.x = pack_bf16x2(x[0], x[1]);
+      o.y = pack_bf16x2(x[2], x[3]);
+      o.z = pack_bf16x2(x[4], x[5]);
+      o.w = pack_bf16x2(x[6], x[7]);
+      *reinterpret_cast<uint4*>(orow + v * 8) = o;
+    }
+  }
+}
+
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
@@ -142,47 +190,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c * 32, r);
         tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row < M && col0 < N) {
-          __nv_bfloat16* orow = out + int64_t(row) * ldo + col0;
-          const __nv_bfloat16* rrow = (EPI == GEMM_EPI_BIAS_RESIDUAL) ? residual + int64_t(row) * ldr + col0 : nullptr;
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {  // 8 columns (16 bytes) per store
-            if (col0 + v * 8 < N) {
-              float x[8];
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + v * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + v * 8 + 4));
-              x[0] = __uint_as_float(r[v * 8 + 0]) + b0.x;
-              x[1] = __uint_as_float(r[v * 8 + 1]) + b0.y;
-              x[2] = __uint_as_float(r[v * 8 + 2]) + b0.z;
-              x[3] = __uint_as_float(r[v * 8 + 3]) + b0.w;
-              x[4] = __uint_as_float(r[v * 8 + 4]) + b1.x;
-              x[5] = __uint_as_float(r[v * 8 + 5]) + b1.y;
-              x[6] = __uint_as_float(r[v * 8 + 6]) + b1.z;
-              x[7] = __uint_as_float(r[v * 8 + 7]) + b1.w;
-              if (EPI == GEMM_EPI_BIAS_GELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
-              }
-              if (EPI == GEMM_EPI_BIAS_RESIDUAL) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(rrow + v * 8);
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-                  x[2 * j] += __bfloat162float(p.x);
-                  x[2 * j + 1] += __bfloat162float(p.y);
-                }
-              }
-              uint4 o;
-              o.x = pack_bf16x2(x[0], x[1]);
-              o.y = pack_bf16x2(x[2], x[3]);
-              o.z = pack_bf16x2(x[4], x[5]);
-              o.w = pack_bf16x2(x[6], x[7]);
-              *reinterpret_cast<uint4*>(orow + v * 8) = o;
-            }
-          }
-        }
+        epilogue_chunk<EPI>(r, row, n0 + c * 32, M, N, bias, residual, ldr, out, ldo);
       }
       tc_fence_before();
       __syncwarp();
@@ -225,21 +233,200 @@ static int launch_gemm_e(int epi, const CUtensorMap& tm_a, const CUtensorMap& tm
   return fail(CRAG_ERR_INVALID, "gemm: unknown epilogue %d", epi);
 }
 
+
+// ---------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs owns a 256 x BN output tile.  Each CTA TMA-loads its own
+// 128 rows of A and HALF of the W tile (BN/2 rows); the leader's single tcgen05.mma.cta_group::2 reads both CTAs'
+// shared memory and accumulates rows 0-127 into the leader's TMEM and rows 128-255 into the peer's.  L2->SM traffic
+// per flop drops by 1/3 against the 128 x 256 single-CTA tile (the W tile is fetched once per pair), which is what
+// bounds the single-CTA kernel.  EPI_WARPS = 4 or 8 (8: two warps per TMEM lane quadrant, half the columns each).
+template <int BN, int STAGES>
+struct Gemm2Layout {
+  static constexpr int kABytes = 128 * kGemmBK * 2;         // this CTA's 128 rows of A
+  static constexpr int kBBytes = (BN / 2) * kGemmBK * 2;    // this CTA's half of the W tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr size_t smem_bytes() { return 1024 + size_t(STAGES) * kStageBytes + (2 * STAGES + 4) * 8 + 16; }
+};
+
+template <int BN, int STAGES, int EPI, int EPI_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
+                  int K, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, int64_t ldr,
+                  __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  using L = Gemm2Layout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStageBytes);
+  uint64_t* bar_empty = bar_full + STAGES;
+  uint64_t* bar_tfull = bar_empty + STAGES;  // [2]
+  uint64_t* bar_tempty = bar_tfull + 2;      // [2]  (used in the leader only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int m_tiles = (M + 255) / 256;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + kGemmBK - 1) / kGemmBK;
+  constexpr uint32_t kTmemCols = 2 * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bar_full[s], 1);   // leader: one arrive.expect_tx, bytes from both CTAs' TMA
+      mbar_init(&bar_empty[s], 1);  // multicast tcgen05.commit from the leader
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bar_tfull[a], 1);
+      mbar_init(&bar_tempty[a], 2 * EPI_WARPS);  // every epilogue warp of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint64_t pol_a = policy_evict_first(), pol_w = policy_evict_last();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          if (leader) mbar_arrive_expect_tx(&bar_full[stage], 2 * L::kStageBytes);
+          tma_load_2d_2cta(&tm_a, &bar_full[stage], sa, kb * kGemmBK, m_blk * 256 + int(cta) * 128, pol_a);
+          tma_load_2d_2cta(&tm_b, &bar_full[stage], sa + L::kABytes, kb * kGemmBK, n_blk * BN + int(cta) * (BN / 2), pol_w);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(256, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+          for (int ks = 0; ks < kGemmBK / 16; ++ks)
+            umma_f16_2cta(d_tmem, umma_desc_k_sw128(a_addr + ks * 32), umma_desc_k_sw128(b_addr + ks * 32), idesc,
+                          (kb | ks) != 0);
+          umma_commit_2cta_mc(&bar_empty[stage], 3);  // frees the slot in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta_mc(&bar_tfull[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    constexpr int kColsPerWarp = BN / (EPI_WARPS / 4);
+    const int col_begin = ((warp - 2) >> 2) * kColsPerWarp;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      const int row = m_blk * 256 + int(cta) * 128 + quad * 32 + lane;
+      const int n0 = n_blk * BN + col_begin;
+      mbar_wait(&bar_tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + col_begin;
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        epilogue_chunk<EPI>(r, row, n0 + c * 32, M, N, bias, residual, ldr, out, ldo);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&bar_tempty[acc]);
+        else mbar_arrive_remote(&bar_tempty[acc], 0);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's smem/TMEM stay alive until the leader's last MMA has been consumed
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, kTmemCols);
+}
+
+template <int BN, int STAGES, int EPI, int EPI_WARPS>
+static int launch_gemm2_t(const CUtensorMap& tm_a, const CUtensorMap& tm_b, int M, int N, int K, const float* bias,
+                          const __nv_bfloat16* residual, int64_t ldr, __nv_bfloat16* out, int64_t ldo,
+                          cudaStream_t stream) {
+  using L = Gemm2Layout<BN, STAGES>;
+  auto kern = gemm2_bf16_kernel<BN, STAGES, EPI, EPI_WARPS>;
+  CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L::smem_bytes())));
+  const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int pairs = sms / 2;
+  if (tiles < pairs) pairs = tiles;
+  kern<<<2 * pairs, 64 + 32 * EPI_WARPS, L::smem_bytes(), stream>>>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo);
+  CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm2_e(int epi, const CUtensorMap& tm_a, const CUtensorMap& tm_b, int M, int N, int K,
+                          const float* bias, const __nv_bfloat16* residual, int64_t ldr, __nv_bfloat16* out,
+                          int64_t ldo, cudaStream_t stream) {
+  switch (epi) {
+    case GEMM_EPI_BIAS: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS, 4>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
+    case GEMM_EPI_BIAS_GELU: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS_GELU, 8>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
+    case GEMM_EPI_BIAS_RESIDUAL: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS_RESIDUAL, 8>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
+  }
+  return fail(CRAG_ERR_INVALID, "gemm: unknown epilogue %d", epi);
+}
+
 int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias, const void* residual,
-              int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int epi, cudaStream_t stream) {
+              int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int epi, cudaStream_t stream, int variant) {
   if (M <= 0) return CRAG_OK;
   if (N < 8 || K < 8 || N % 8 != 0 || K % 8 != 0) return fail(CRAG_ERR_INVALID, "gemm: N and K must be positive multiples of 8 (N=%d K=%d)", N, K);
   if (lda % 8 || ldw % 8 || ldo % 8 || (epi == GEMM_EPI_BIAS_RESIDUAL && ldr % 8)) return fail(CRAG_ERR_INVALID, "gemm: leading dimensions must be multiples of 8 elements");
   if (!a || !w || !bias || !out || (epi == GEMM_EPI_BIAS_RESIDUAL && !residual)) return fail(CRAG_ERR_INVALID, "gemm: null pointer");
   if ((uintptr_t(a) | uintptr_t(w) | uintptr_t(out) | uintptr_t(bias) | uintptr_t(residual)) & 15) return fail(CRAG_ERR_INVALID, "gemm: pointers must be 16-byte aligned");
   const bool wide = (N % 256 == 0) || N >= 1024;
+  const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(residual);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   CUtensorMap tm_a, tm_b;
   int rc = make_tmap_bf16_2d(&tm_a, a, uint64_t(M), uint64_t(K), uint64_t(lda) * 2, kGemmBM);
   if (rc != CRAG_OK) return rc;
+  if (M > 128 && !(variant & 1)) {
+    // CTA-pair kernel: each CTA fetches half of the W tile
+    rc = make_tmap_bf16_2d(&tm_b, w, uint64_t(N), uint64_t(K), uint64_t(ldw) * 2, wide ? 128 : 64);
+    if (rc != CRAG_OK) return rc;
+    if (wide) return launch_gemm2_e<256, 6>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
+    return launch_gemm2_e<128, 8>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
+  }
   rc = make_tmap_bf16_2d(&tm_b, w, uint64_t(N), uint64_t(K), uint64_t(ldw) * 2, wide ? 256 : 128);
   if (rc != CRAG_OK) return rc;
-  const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(residual);
-  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   if (wide) return launch_gemm_e<256, 4>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
   return launch_gemm_e<128, 6>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
 }
@@ -249,6 +436,7 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const floa
 extern "C" int crag_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias,
                               const void* residual, int64_t ldr, void* out, int64_t ldo, int m, int n, int k,
                               int epilogue, crag_stream_t stream) {
-  return crag::gemm_bf16(a, lda, w, ldw, bias, residual, ldr, out, ldo, m, n, k, epilogue,
-                         static_cast<cudaStream_t>(stream));
+  // bits 8+ of `epilogue` select a kernel variant for A/B testing (0 = default dispatch, 1 = force single-CTA)
+  return crag::gemm_bf16(a, lda, w, ldw, bias, residual, ldr, out, ldo, m, n, k, epilogue & 0xFF,
+                         static_cast<cudaStream_t>(stream), epilogue >> 8);
 }

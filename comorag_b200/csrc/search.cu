@@ -11,8 +11,9 @@
 //            (16 KB, 128-byte swizzle) through a STAGES-deep mbarrier ring; the
 //            32 x dim query block is TMA-staged once and stays in smem.
 //   warp 1   tcgen05.mma issuer: scores[128 rows, 32 queries] accumulate in
-//            TMEM (fp32) over dim/16 UMMA steps; two accumulator buffers so the
-//            next tile's MMAs overlap this tile's select.
+//            TMEM (fp32) over dim/16 UMMA steps; 16 score-tile buffers (all 512
+//            TMEM columns) so the HBM stream keeps running while the select warps
+//            are busy sorting a full candidate buffer.
 //   warps 2-5  select: each thread owns one corpus row of the tile (one TMEM
 //            lane), reads its 32 scores with tcgen05.ld, updates per-query
 //            min/max in registers and offers scores that beat the query's
@@ -32,14 +33,15 @@ constexpr int kStageBytes = kTileRows * kBlockK * 2;  // 16 KB
 constexpr int kQBlockBytes = kNQ * kBlockK * 2;       // 4 KB
 constexpr int kSearchThreads = 192;
 constexpr int kEpiThreads = 128;
-constexpr uint32_t kTmemCols = 64;  // 2 accumulator buffers x 32 columns
+constexpr int kAccStages = 16;       // score-tile buffers in TMEM: the scan may run 16 tiles ahead of the select warps
+constexpr uint32_t kTmemCols = kAccStages * kNQ;  // 512 columns = all of TMEM (1 CTA per SM)
 
 template <int KLIST, int CAP, int STAGES>
 struct SearchLayout {
   static constexpr int kKeysPerQuery = KLIST + CAP;
   __host__ __device__ static constexpr size_t keys_bytes() { return size_t(kNQ) * kKeysPerQuery * 8; }
   __host__ __device__ static constexpr size_t misc_bytes() {
-    return (2 * STAGES + 5) * 8    // mbarriers
+    return (2 * STAGES + 2 * kAccStages + 1) * 8    // mbarriers
            + kNQ * 8               // thr_key
            + kNQ * 4               // thr_f
            + kNQ * 4               // cnt
@@ -65,9 +67,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   uint64_t* keys = reinterpret_cast<uint64_t*>(q_base + num_kb * kQBlockBytes);
   uint64_t* bar_full = keys + kNQ * L::kKeysPerQuery;
   uint64_t* bar_empty = bar_full + STAGES;
-  uint64_t* bar_tfull = bar_empty + STAGES;   // [2]
-  uint64_t* bar_tempty = bar_tfull + 2;       // [2]
-  uint64_t* bar_q = bar_tempty + 2;           // [1]
+  uint64_t* bar_tfull = bar_empty + STAGES;            // [kAccStages]
+  uint64_t* bar_tempty = bar_tfull + kAccStages;       // [kAccStages]
+  uint64_t* bar_q = bar_tempty + kAccStages;           // [1]
   uint64_t* thr_key = bar_q + 1;              // [kNQ]
   float* thr_f = reinterpret_cast<float*>(thr_key + kNQ);  // [kNQ]
   int* cnt = reinterpret_cast<int*>(thr_f + kNQ);          // [kNQ]
@@ -86,7 +88,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < kAccStages; ++a) {
       mbar_init(&bar_tfull[a], 1);
       mbar_init(&bar_tempty[a], 4);  // one arrive per select warp
     }
@@ -155,8 +157,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&bar_tfull[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -178,8 +179,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
 
       const int row = tile * kTileRows + quad * 32 + lane;
       uint32_t pending = 0;

@@ -14,10 +14,12 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GEMM_CASES = [  # M, N, K, epi
-    (128, 128, 64, 0), (128, 256, 128, 0), (300, 384, 384, 0), (1000, 1152, 384, 0), (777, 1536, 384, 1),
-    (512, 384, 1536, 2), (4096, 3072, 1024, 0), (4096, 1024, 1024, 2), (4096, 4096, 1024, 1), (4096, 1024, 4096, 2),
-    (16384, 4096, 1024, 1),
+GEMM_CASES = [  # M, N, K, epi, variant (0 = default dispatch: CTA-pair kernel when M > 128; 1 = force single-CTA)
+    (128, 128, 64, 0, 0), (129, 256, 128, 0, 0), (255, 128, 64, 2, 0), (257, 384, 384, 1, 0), (300, 384, 384, 0, 0),
+    (1000, 1152, 384, 0, 0), (777, 1536, 384, 1, 0), (512, 384, 1536, 2, 0),
+    (16384, 3072, 1024, 0, 0), (16384, 3072, 1024, 0, 1), (16384, 1024, 1024, 2, 0), (16384, 1024, 1024, 2, 1),
+    (16384, 4096, 1024, 1, 0), (16384, 4096, 1024, 1, 1), (16384, 1024, 4096, 2, 0), (16384, 1024, 4096, 2, 1),
+    (16384, 1152, 384, 0, 0), (16384, 384, 1536, 2, 0), (16384, 768, 3072, 2, 0),
 ]
 ATTN_CASES = [  # H, heads, lengths
     (128, 4, [5, 64, 65, 1, 130]), (1024, 16, [512, 33, 200, 512]), (384, 12, [77, 512, 300]), (768, 12, [128] * 6),
@@ -35,7 +37,7 @@ def gemm_case(i):
     import torch
     from comorag_b200 import _native
     lib = _native.load()
-    M, N, K, epi = GEMM_CASES[i]
+    M, N, K, epi, variant = GEMM_CASES[i]
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(i)
     a = (torch.randn(M, K, generator=g, device=dev) * 0.5).bfloat16()
@@ -47,7 +49,7 @@ def gemm_case(i):
 
     def run():
         rc = lib.crag_gemm_bf16(a.data_ptr(), K, w.data_ptr(), K, bias.data_ptr(), res.data_ptr(), N, out.data_ptr(), N,
-                                M, N, K, epi, st)
+                                M, N, K, epi | (variant << 8), st)
         _native.check(rc, "crag_gemm_bf16")
     run()
     torch.cuda.synchronize()
@@ -58,7 +60,7 @@ def gemm_case(i):
         ref = ref + res.float()
     err = (out.float() - ref).abs()
     tol = 0.01 * ref.abs() + 0.02
-    r = {"kind": "gemm", "shape": [M, N, K, epi], "max_err": float(err.max()), "ok": bool((err <= tol).all()),
+    r = {"kind": "gemm", "shape": [M, N, K, epi], "variant": variant, "max_err": float(err.max()), "ok": bool((err <= tol).all()),
          "bad_frac": float((err > tol).float().mean())}
     if M >= 4096:
         for _ in range(3):
