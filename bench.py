@@ -60,6 +60,18 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def scan_traffic(rows: int, dim: int, nq: int, k: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch from the committed `ncu --set full` capture
+    (profiles/search_traffic.json), if one exists for exactly this shard shape; else None."""
+    p = os.path.join(ROOT, "profiles", "search_traffic.json")
+    if not os.path.exists(p):
+        return None
+    for e in json.load(open(p)):
+        if (e["rows"], e["dim"], e["nq"], e["k"]) == (rows, dim, nq, k):
+            return e["dram_bytes"]
+    return None
+
+
 # ------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
     """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
@@ -76,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -324,7 +336,6 @@ def run_ours(args):
     scan_avg = sum(scan_ms) / len(scan_ms)
     algo_bytes = float(my_rows) * args.dim * 2
     achieved = algo_bytes / scan_avg / 1e6  # GB/s
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e through the host API
     for _ in range(3):
@@ -382,6 +393,8 @@ def run_ours(args):
                   "gpu_launches": args.encode_steps * (2 + cfg.num_hidden_layers * 7)}
         del enc
 
+    # the sampler has been running through every GPU-timed phase above (search value, scan roofline, e2e, encode)
+    clocks = sampler.stop() if rank == 0 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rows = pick_cpu_rows(args.rows, args.dim, args.cpu_budget_s)
@@ -406,7 +419,8 @@ def run_ours(args):
             "gpu_launches": args.steps * launches_per_step,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": scan_traffic(my_rows, args.dim, args.nq, args.k),
+                         "peak_source": peaks["source"],
                          "kernel": "search_topk_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                          "kernel_ms": scan_avg},
             "cpu_baseline": cpu,

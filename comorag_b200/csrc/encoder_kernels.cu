@@ -326,25 +326,26 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
 }
 
 // ----------------------------------------------------------- pool + normalise
-// one block (128 threads) per sequence; thread owns 8-column vectors
-__global__ void __launch_bounds__(128) pool_normalize_kernel(const __nv_bfloat16* __restrict__ hidden,
-                                                             const int32_t* __restrict__ cu_seqlens, int H,
-                                                             int normalize, float* __restrict__ out_f32,
-                                                             __nv_bfloat16* __restrict__ out_bf16,
-                                                             int64_t out_bf16_stride) {
-  __shared__ float s_part[4];
-  const int seq = blockIdx.x, tid = threadIdx.x;
+// one block per sequence: kPoolGroups token groups x 128 column threads (8 bf16 columns each, up to 2 vectors:
+// H <= 2048); groups stride over the tokens, partial sums meet in shared memory.
+constexpr int kPoolGroups = 8;
+__global__ void __launch_bounds__(128 * kPoolGroups) pool_normalize_kernel(const __nv_bfloat16* __restrict__ hidden,
+                                                                           const int32_t* __restrict__ cu_seqlens, int H,
+                                                                           int normalize, float* __restrict__ out_f32,
+                                                                           __nv_bfloat16* __restrict__ out_bf16,
+                                                                           int64_t out_bf16_stride) {
+  extern __shared__ float s_pool[];            // [kPoolGroups][H] partial sums, then [4] norm partials
+  const int seq = blockIdx.x;
+  const int tid = threadIdx.x & 127, grp = threadIdx.x >> 7;
   const int start = __ldg(cu_seqlens + seq);
   const int L = __ldg(cu_seqlens + seq + 1) - start;
   const int nvec = H / 8;
-  float ss = 0.f;
-  // each thread accumulates up to 2 vectors (H <= 2048)
   float acc[2][8];
 #pragma unroll
   for (int v = 0; v < 2; ++v)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
-  for (int t = 0; t < L; ++t) {
+  for (int t = grp; t < L; t += kPoolGroups) {
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       const int vec = tid + v * 128;
@@ -356,18 +357,34 @@ __global__ void __launch_bounds__(128) pool_normalize_kernel(const __nv_bfloat16
       }
     }
   }
-  const float inv_len = 1.f / float(L);  // L == 0 -> inf/nan row, as the reference's 0/0 would give
 #pragma unroll
-  for (int v = 0; v < 2; ++v)
+  for (int v = 0; v < 2; ++v) {
+    const int vec = tid + v * 128;
+    if (vec < nvec)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_pool[grp * H + vec * 8 + j] = acc[v][j];
+  }
+  __syncthreads();
+  if (grp != 0) return;
+  const float inv_len = 1.f / float(L);  // L == 0 -> inf/nan row, as the reference's 0/0 would give
+  float ss = 0.f;
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const int vec = tid + v * 128;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      acc[v][j] *= inv_len;
-      if (tid + v * 128 < nvec) ss += acc[v][j] * acc[v][j];
+      float sum = 0.f;
+      if (vec < nvec)
+        for (int g2 = 0; g2 < kPoolGroups; ++g2) sum += s_pool[g2 * H + vec * 8 + j];  // fixed order: deterministic
+      acc[v][j] = sum * inv_len;
+      ss += acc[v][j] * acc[v][j];
     }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  float* s_part = s_pool + kPoolGroups * H;
   if ((tid & 31) == 0) s_part[tid >> 5] = ss;
-  __syncthreads();
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // group 0 only
   const float norm = sqrtf(s_part[0] + s_part[1] + s_part[2] + s_part[3]);
   const float inv = normalize ? 1.f / fmaxf(norm, 1e-12f) : 1.f;  // F.normalize eps
 #pragma unroll
@@ -446,8 +463,11 @@ int launch_pool_normalize(const void* hidden, const int32_t* cu_seqlens, int n_s
                           float* out_f32, void* out_bf16, int64_t out_bf16_stride, cudaStream_t stream) {
   if (n_seqs <= 0) return CRAG_OK;
   if (H > 2048) return fail(CRAG_ERR_UNSUPPORTED, "hidden size %d > 2048 not supported", H);
-  pool_normalize_kernel<<<n_seqs, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(hidden), cu_seqlens, H, normalize,
-                                                    out_f32, static_cast<__nv_bfloat16*>(out_bf16), out_bf16_stride);
+  const size_t smem = (size_t(kPoolGroups) * H + 4) * sizeof(float);
+  if (smem > 48 * 1024) CRAG_CUDA_OK(cudaFuncSetAttribute(pool_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  pool_normalize_kernel<<<n_seqs, 128 * kPoolGroups, smem, stream>>>(static_cast<const __nv_bfloat16*>(hidden), cu_seqlens, H,
+                                                                     normalize, out_f32, static_cast<__nv_bfloat16*>(out_bf16),
+                                                                     out_bf16_stride);
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }

@@ -297,6 +297,21 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
 
   int c = 0;
   const int total = parts * k;
+  // Admission bound before any sorting: every part's list is sorted, so its k-th entry is a lower bound of the
+  // global k-th best (that part alone already holds k candidates at least that good).  Taking the max over parts
+  // rejects almost all of the parts*k candidates up front and leaves one flush for the common case.
+  uint64_t bound = 0;
+  if (!PAIRS) {
+    for (int p = lane; p < parts; p += 32) {
+      const uint64_t kth = part_keys[(size_t(p) * q_stride + q) * k + (k - 1)];
+      bound = kth > bound ? kth : bound;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint64_t other = shfl_xor_u64(bound, o);
+      bound = other > bound ? other : bound;
+    }
+  }
   for (int base = 0; base < total; base += 32) {
     const int idx = base + lane;
     uint64_t key = 0;
@@ -309,7 +324,8 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
         key = part_keys[(size_t(p) * q_stride + q) * k + j];
       }
     }
-    const bool take = key != 0 && key > s_thr[w];
+    const uint64_t thr = s_thr[w] > bound ? s_thr[w] : bound;
+    const bool take = key != 0 && key >= thr;
     const uint32_t m = __ballot_sync(0xffffffffu, take);
     if (take) keys[KLIST + c + __popc(m & ((1u << lane) - 1u))] = key;
     c += __popc(m);
