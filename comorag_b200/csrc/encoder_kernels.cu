@@ -187,19 +187,27 @@ __device__ __forceinline__ void load_tile_async(__nv_bfloat16* smem_tile, const 
   }
 }
 
-// grid = (ceil(max_len/64), heads, n_seqs), block = 128 (4 warps x 16 query rows)
-template <int DH>
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// grid = (ceil(max_len / (64*MT)), heads, n_seqs), block = 128: 4 warps x MT m-tiles of 16 query rows.
+// MT = 2 halves the K/V fragment (ldmatrix) traffic per flop, which co-limits the kernel with the legacy HMMA pipe.
+template <int DH, int MT>
 __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                         const int32_t* __restrict__ cu_seqlens, int H,
                                                         float scale_log2e, __nv_bfloat16* __restrict__ ctx) {
-  __shared__ __align__(128) __nv_bfloat16 sQ[64 * DH];
+  constexpr int BM = 64 * MT;
+  __shared__ __align__(128) __nv_bfloat16 sQ[BM * DH];
   __shared__ __align__(128) __nv_bfloat16 sK[2][64 * DH];
   __shared__ __align__(128) __nv_bfloat16 sV[2][64 * DH];
 
   const int seq = blockIdx.z, head = blockIdx.y;
   const int start = __ldg(cu_seqlens + seq);
   const int L = __ldg(cu_seqlens + seq + 1) - start;
-  const int q0 = blockIdx.x * 64;
+  const int q0 = blockIdx.x * BM;
   if (q0 >= L) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -209,18 +217,24 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
   const __nv_bfloat16* vbase = qbase + 2 * H;
   const int n_kv = (L + 63) / 64;
 
-  load_tile_async<DH>(sQ, qbase, ld, q0, L, tid);
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) load_tile_async<DH>(sQ + mt * 64 * DH, qbase, ld, q0 + mt * 64, L, tid);
   load_tile_async<DH>(sK[0], kbase, ld, 0, L, tid);
   load_tile_async<DH>(sV[0], vbase, ld, 0, L, tid);
   cp_async_commit();
 
   constexpr int KS = DH / 16;  // k-steps over the head dim
   constexpr int NT = DH / 8;   // output n-tiles over the head dim
-  uint32_t qf[KS][4];
-  float o[NT][4];
+  uint32_t qf[MT][KS][4];
+  float o[MT][NT][4];
+  float m_run[MT][2], l_run[MT][2];
 #pragma unroll
-  for (int n = 0; n < NT; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int n = 0; n < NT; ++n) o[mt][n][0] = o[mt][n][1] = o[mt][n][2] = o[mt][n][3] = 0.f;
+    m_run[mt][0] = m_run[mt][1] = -INFINITY;
+    l_run[mt][0] = l_run[mt][1] = 0.f;
+  }
 
   for (int j = 0; j < n_kv; ++j) {
     const int buf = j & 1;
@@ -234,14 +248,19 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
     }
     __syncthreads();
     if (j == 0) {
+      // warp w owns query rows [w*16*MT, (w+1)*16*MT) of the CTA tile
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
-        ldmatrix_x4(qf[ks], tile_ptr<DH>(sQ, warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4)));
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          ldmatrix_x4(qf[mt][ks], tile_ptr<DH>(sQ, (warp * MT + mt) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4)));
     }
-    // S = Q K^T : 16 x 64 per warp
-    float s[8][4];
+    // S = Q K^T : (16*MT) x 64 per warp
+    float s[MT][8][4];
 #pragma unroll
-    for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int n = 0; n < 8; ++n) s[mt][n][0] = s[mt][n][1] = s[mt][n][2] = s[mt][n][3] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
@@ -249,50 +268,56 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
         uint32_t kf[4];
         // matrices: (keys np*16+0..7, d ks*16+0..7), (same keys, d +8), (keys +8, d 0..7), (keys +8, d +8)
         ldmatrix_x4(kf, tile_ptr<DH>(sK[buf], np * 16 + (lane & 7) + (lane >> 4) * 8, ks * 2 + ((lane >> 3) & 1)));
-        mma_bf16_16816(s[np * 2], qf[ks], kf[0], kf[1]);
-        mma_bf16_16816(s[np * 2 + 1], qf[ks], kf[2], kf[3]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16_16816(s[mt][np * 2], qf[mt][ks], kf[0], kf[1]);
+          mma_bf16_16816(s[mt][np * 2 + 1], qf[mt][ks], kf[2], kf[3]);
+        }
       }
     }
     // mask keys beyond the sequence, online softmax (base-2 domain)
     const int kbase_idx = j * 64;
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+    const bool ragged = kbase_idx + 64 > L;
+    uint32_t pf[MT][4][4];  // P as A fragments: 4 k-steps of 16 keys
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
+    for (int mt = 0; mt < MT; ++mt) {
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = kbase_idx + n * 8 + t4 * 2 + (e & 1);
-        float v = s[n][e] * scale_log2e;
-        if (key >= L) v = -INFINITY;
-        s[n][e] = v;
+      for (int n = 0; n < 8; ++n) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float v = s[mt][n][e] * scale_log2e;
+          if (ragged && kbase_idx + n * 8 + t4 * 2 + (e & 1) >= L) v = -INFINITY;
+          s[mt][n][e] = v;
+        }
+        mx0 = fmaxf(mx0, fmaxf(s[mt][n][0], s[mt][n][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[mt][n][2], s[mt][n][3]));
       }
-      mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float nm0 = fmaxf(m0, mx0), nm1 = fmaxf(m1, mx1);  // finite: every tile has >= 1 valid key
-    const float c0 = exp2f(m0 - nm0), c1 = exp2f(m1 - nm1);
-    m0 = nm0;
-    m1 = nm1;
-    float rs0 = 0.f, rs1 = 0.f;
-    uint32_t pf[4][4];  // P as A fragments: 4 k-steps of 16 keys
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float nm0 = fmaxf(m_run[mt][0], mx0), nm1 = fmaxf(m_run[mt][1], mx1);  // finite: >= 1 valid key per tile
+      const float c0 = fast_exp2(m_run[mt][0] - nm0), c1 = fast_exp2(m_run[mt][1] - nm1);
+      m_run[mt][0] = nm0;
+      m_run[mt][1] = nm1;
+      float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const float p0 = exp2f(s[n][0] - m0), p1 = exp2f(s[n][1] - m0);
-      const float p2 = exp2f(s[n][2] - m1), p3 = exp2f(s[n][3] - m1);
-      rs0 += p0 + p1;
-      rs1 += p2 + p3;
-      __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
-      pf[n >> 1][(n & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&lo);
-      pf[n >> 1][(n & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
-    }
-    l0 = l0 * c0 + rs0;
-    l1 = l1 * c1 + rs1;
+      for (int n = 0; n < 8; ++n) {
+        const float p0 = fast_exp2(s[mt][n][0] - nm0), p1 = fast_exp2(s[mt][n][1] - nm0);
+        const float p2 = fast_exp2(s[mt][n][2] - nm1), p3 = fast_exp2(s[mt][n][3] - nm1);
+        rs0 += p0 + p1;
+        rs1 += p2 + p3;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+        pf[mt][n >> 1][(n & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&lo);
+        pf[mt][n >> 1][(n & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+      }
+      l_run[mt][0] = l_run[mt][0] * c0 + rs0;
+      l_run[mt][1] = l_run[mt][1] * c1 + rs1;
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1;
+      for (int n = 0; n < NT; ++n) {
+        o[mt][n][0] *= c0; o[mt][n][1] *= c0; o[mt][n][2] *= c1; o[mt][n][3] *= c1;
+      }
     }
     // O += P V
 #pragma unroll
@@ -302,26 +327,32 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
         uint32_t vf[4];
         // .trans matrices: (keys kk*16+0..7, d dp*16+0..7), (keys +8, same d), (keys 0..7, d +8), (keys +8, d +8)
         ldmatrix_x4_trans(vf, tile_ptr<DH>(sV[buf], kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 2 + (lane >> 4)));
-        mma_bf16_16816(o[dp * 2], pf[kk], vf[0], vf[1]);
-        mma_bf16_16816(o[dp * 2 + 1], pf[kk], vf[2], vf[3]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16_16816(o[mt][dp * 2], pf[mt][kk], vf[0], vf[1]);
+          mma_bf16_16816(o[mt][dp * 2 + 1], pf[mt][kk], vf[2], vf[3]);
+        }
       }
     }
     __syncthreads();  // all warps done with buf before it is refilled
   }
-  // row sums live distributed over the 4 lanes of a quad
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
-  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
 #pragma unroll
-  for (int n = 0; n < NT; ++n) {
-    const int col = head * DH + n * 8 + t4 * 2;
-    if (r0 < L)
-      *reinterpret_cast<__nv_bfloat162*>(ctx + int64_t(start + r0) * H + col) = __floats2bfloat162_rn(o[n][0] * inv0, o[n][1] * inv0);
-    if (r1 < L)
-      *reinterpret_cast<__nv_bfloat162*>(ctx + int64_t(start + r1) * H + col) = __floats2bfloat162_rn(o[n][2] * inv1, o[n][3] * inv1);
+  for (int mt = 0; mt < MT; ++mt) {
+    float l0 = l_run[mt][0], l1 = l_run[mt][1];  // row sums live distributed over the 4 lanes of a quad
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    const int r0 = q0 + (warp * MT + mt) * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const int col = head * DH + n * 8 + t4 * 2;
+      if (r0 < L)
+        *reinterpret_cast<__nv_bfloat162*>(ctx + int64_t(start + r0) * H + col) = __floats2bfloat162_rn(o[mt][n][0] * inv0, o[mt][n][1] * inv0);
+      if (r1 < L)
+        *reinterpret_cast<__nv_bfloat162*>(ctx + int64_t(start + r1) * H + col) = __floats2bfloat162_rn(o[mt][n][2] * inv1, o[mt][n][3] * inv1);
+    }
   }
 }
 
@@ -448,13 +479,19 @@ int launch_attention(const void* qkv, const int32_t* cu_seqlens, int n_seqs, int
                      cudaStream_t stream) {
   if (n_seqs <= 0 || max_len <= 0) return CRAG_OK;
   const int dh = H / heads;
-  const dim3 grid((max_len + 63) / 64, heads, n_seqs);
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(dh));
   const auto* q = static_cast<const __nv_bfloat16*>(qkv);
   auto* c = static_cast<__nv_bfloat16*>(ctx);
-  if (dh == 64) attention_kernel<64><<<grid, 128, 0, stream>>>(q, cu_seqlens, H, scale_log2e, c);
-  else if (dh == 32) attention_kernel<32><<<grid, 128, 0, stream>>>(q, cu_seqlens, H, scale_log2e, c);
-  else return fail(CRAG_ERR_UNSUPPORTED, "head dim %d not supported (32 or 64)", dh);
+  if (dh != 64 && dh != 32) return fail(CRAG_ERR_UNSUPPORTED, "head dim %d not supported (32 or 64)", dh);
+  if (max_len > 64) {  // 128-query tiles: 2 m-tiles per warp
+    const dim3 grid((max_len + 127) / 128, heads, n_seqs);
+    if (dh == 64) attention_kernel<64, 2><<<grid, 128, 0, stream>>>(q, cu_seqlens, H, scale_log2e, c);
+    else attention_kernel<32, 2><<<grid, 128, 0, stream>>>(q, cu_seqlens, H, scale_log2e, c);
+  } else {
+    const dim3 grid(1, heads, n_seqs);
+    if (dh == 64) attention_kernel<64, 1><<<grid, 128, 0, stream>>>(q, cu_seqlens, H, scale_log2e, c);
+    else attention_kernel<32, 1><<<grid, 128, 0, stream>>>(q, cu_seqlens, H, scale_log2e, c);
+  }
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }
