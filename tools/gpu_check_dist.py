@@ -1,0 +1,47 @@
+"""Multi-GPU check (run under torchrun, one rank per GPU): the row-sharded search (local fused scan + ONE NCCL
+all-gather + merge kernel) returns on EVERY rank exactly what one GPU returns for the unsharded corpus.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/gpu_check_dist.py
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch
+import torch.distributed as dist
+
+
+def main():
+    from comorag_b200.dist import ShardedIndex, shard_bounds
+    from comorag_b200.index import DenseIndex
+    from util_search import make_unit_rows
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    results = []
+    for n, dim, nq, k in [(100_003, 1024, 32, 10), (5, 64, 3, 10), (40_000, 768, 40, 100), (1_000_000, 1024, 32, 10)]:
+        corpus = make_unit_rows(n, dim, 77, device=dev)          # identical on every rank (same seed, same device type)
+        queries = make_unit_rows(nq, dim, 78, device=dev)
+        offs = shard_bounds(n, world)
+        shard = corpus[offs[rank]:offs[rank + 1]].contiguous()
+        idx = ShardedIndex(DenseIndex.from_tensor(shard, row_offset=offs[rank]) if shard.shape[0] else DenseIndex(dim, device=dev, row_offset=offs[rank]))
+        ids, scores, mm = idx.search_device(queries, k)
+        w_ids, w_scores, w_mm = DenseIndex.from_tensor(corpus).search_device(queries, k)
+        ok = bool(torch.equal(ids, w_ids) and torch.equal(scores, w_scores) and torch.equal(mm, w_mm))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        results.append({"shape": [n, dim, nq, k], "world": world, "all_ranks_equal_single_gpu": bool(flag.item())})
+    if rank == 0:
+        print("RESULT " + json.dumps(results))
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(results, open(os.path.join(ROOT, "gpurun_out", f"check_dist_w{world}.json"), "w"))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
