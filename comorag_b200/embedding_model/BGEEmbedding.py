@@ -58,6 +58,13 @@ class BGEEmbeddingModel(BaseEmbeddingModel):
         self.embedding_dim = self.embedding_model.config.hidden_size
         self._token_budget = int(cfg_get(self.global_config, "embedding_token_budget", 16384))
         self._tok_lock = threading.Lock()  # HF fast tokenizers are not re-entrant across threads
+        # optional dynamic batching of concurrent callers (ComoRAG.py:436-441 runs <=16 threads); off by default
+        self._coalescer = None
+        if cfg_get(self.global_config, "embedding_coalesce", False):
+            from ..coalescer import CoalescedEncode
+            self._coalescer = CoalescedEncode(
+                self._encode_direct, max_texts=int(cfg_get(self.global_config, "embedding_coalesce_max_texts", 64)),
+                max_wait_s=float(cfg_get(self.global_config, "embedding_coalesce_wait_ms", 0.3)) * 1e-3)
         if cfg_get(self.global_config, "embedding_cache_enabled", False):
             cache_path = cfg_get(self.global_config, "embedding_cache_path", "bge_embeddings_cache.db")
             self.encode = make_cache_embed(self._encode, cache_path, self.device)
@@ -91,6 +98,14 @@ class BGEEmbeddingModel(BaseEmbeddingModel):
 
     def _encode(self, prompts: Union[str, List[str]], **kwargs) -> torch.Tensor:
         """BGEEmbedding.py:92-129: [instruction +] text -> tokenizer -> encoder -> mean pool -> (normalise)."""
+        if self._coalescer is None:
+            return self._encode_direct(prompts, **kwargs)
+        return self._coalescer.encode(
+            prompts, instruction=kwargs.get("instruction", ""),
+            max_length=kwargs.get("max_length", self.embedding_config.encode_params.get("max_length", 512)),
+            normalize=bool(kwargs.get("normalize", True)))
+
+    def _encode_direct(self, prompts: Union[str, List[str]], **kwargs) -> torch.Tensor:
         if isinstance(prompts, str):
             prompts = [prompts]
         instruction = kwargs.get("instruction", "")

@@ -68,6 +68,10 @@ class EmbeddingStore:
         self._n = 0
         self._index = None  # DenseIndex, created on first use (needs a CUDA device)
         self._index_rows = 0
+        self._search_coalescer = None
+        if getattr(getattr(embedding_model, "global_config", None), "embedding_coalesce", False):
+            from .coalescer import CoalescedSearch
+            self._search_coalescer = CoalescedSearch(lambda: self.index)
         self._load_data()
 
     # ------------------------------------------------------------- bookkeeping
@@ -219,4 +223,6 @@ class EmbeddingStore:
     def search(self, query_embeddings, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """Top-k rows for a block of query embeddings [nq, D] (host or device): (row indices int64 [nq, k]
         into hash_ids/texts, raw inner products [nq, k], (min, max) over all rows [nq, 2])."""
+        if self._search_coalescer is not None:
+            return self._search_coalescer.search(query_embeddings, k)
         return self.index.search(query_embeddings, k)
