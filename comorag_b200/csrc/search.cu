@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
                                                          const int64_t* __restrict__ in_ids,
                                                          const float* __restrict__ part_minmax, int parts,
                                                          int q_stride, int nq, int k, int64_t row_offset,
+                                                         int64_t ids_stride, int64_t scores_stride, int64_t mm_stride,
                                                          int64_t* __restrict__ out_ids,
                                                          float* __restrict__ out_scores,
                                                          float* __restrict__ out_minmax) {
@@ -318,8 +319,10 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
     if (idx < total) {
       const int p = idx / k, j = idx - p * k;
       if (PAIRS) {
-        const size_t at = (size_t(p) * q_stride + q) * k + j;
-        if (in_ids[at] >= 0) key = make_key(in_scores[at], uint32_t(idx));
+        const size_t at = size_t(q) * k + j;
+        const int64_t id = *reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(in_ids + at) + p * ids_stride);
+        const float sc = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(in_scores + at) + p * scores_stride);
+        if (id >= 0) key = make_key(sc, uint32_t(idx));
       } else {
         key = part_keys[(size_t(p) * q_stride + q) * k + j];
       }
@@ -343,8 +346,13 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
     int64_t id = -1;
     if (key) {
       s = key_score(key);
-      id = PAIRS ? in_ids[(size_t(key_id(key) / k) * q_stride + q) * k + key_id(key) % k]
-                 : int64_t(key_id(key)) + row_offset;
+      if (PAIRS) {
+        const uint32_t ci = key_id(key);
+        id = *reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(in_ids + size_t(q) * k + ci % k) +
+                                               int64_t(ci / k) * ids_stride);
+      } else {
+        id = int64_t(key_id(key)) + row_offset;
+      }
     }
     out_scores[size_t(q) * k + j] = s;
     out_ids[size_t(q) * k + j] = id;
@@ -353,8 +361,10 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
     float a = INFINITY, b = -INFINITY;
     if (part_minmax != nullptr) {
       for (int p = lane; p < parts; p += 32) {
-        a = fminf(a, part_minmax[(size_t(p) * q_stride + q) * 2 + 0]);
-        b = fmaxf(b, part_minmax[(size_t(p) * q_stride + q) * 2 + 1]);
+        const float* mm = PAIRS ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(part_minmax + size_t(q) * 2) + p * mm_stride)
+                                : part_minmax + (size_t(p) * q_stride + q) * 2;
+        a = fminf(a, mm[0]);
+        b = fmaxf(b, mm[1]);
       }
     }
 #pragma unroll
@@ -457,9 +467,9 @@ int finalize_pass(const void* workspace, int64_t n_rows, int nq, int k, int64_t 
   const float* part_minmax = reinterpret_cast<const float*>(static_cast<const uint8_t*>(workspace) + plan.keys_bytes);
   const int mgrid = (nq + 3) / 4;
   if (k <= 64)
-    merge_topk_kernel<64, 64, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, out_ids, out_scores, out_minmax);
+    merge_topk_kernel<64, 64, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, 0, 0, 0, out_ids, out_scores, out_minmax);
   else
-    merge_topk_kernel<128, 128, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, out_ids, out_scores, out_minmax);
+    merge_topk_kernel<128, 128, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, 0, 0, 0, out_ids, out_scores, out_minmax);
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }
@@ -507,17 +517,39 @@ extern "C" int crag_search_topk(const void* corpus, int64_t n_rows, int dim, int
   return CRAG_OK;
 }
 
-extern "C" int crag_merge_topk(const float* scores, const int64_t* ids, const float* minmax, int parts, int nq,
-                               int k, int64_t* out_ids, float* out_scores, float* out_minmax,
-                               crag_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+namespace crag {
+namespace {
+int merge_pairs(const float* scores, const int64_t* ids, const float* minmax, int64_t ids_stride, int64_t scores_stride,
+                int64_t mm_stride, int parts, int nq, int k, int64_t* out_ids, float* out_scores, float* out_minmax,
+                cudaStream_t stream) {
   if (parts < 0 || nq < 1 || k < 1 || k > 128 || int64_t(parts) * k > (1 << 20)) return fail(CRAG_ERR_INVALID, "crag_merge_topk: bad sizes (parts=%d nq=%d k=%d)", parts, nq, k);
   if (!out_ids || !out_scores || (parts > 0 && (!scores || !ids))) return fail(CRAG_ERR_INVALID, "crag_merge_topk: null pointer");
   const int mgrid = (nq + 3) / 4;
+  const float* mm = out_minmax ? minmax : nullptr;
   if (k <= 64)
-    merge_topk_kernel<64, 64, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, minmax, parts, nq, nq, k, 0, out_ids, out_scores, out_minmax);
+    merge_topk_kernel<64, 64, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, mm, parts, nq, nq, k, 0, ids_stride, scores_stride, mm_stride, out_ids, out_scores, out_minmax);
   else
-    merge_topk_kernel<128, 128, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, minmax, parts, nq, nq, k, 0, out_ids, out_scores, out_minmax);
+    merge_topk_kernel<128, 128, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, mm, parts, nq, nq, k, 0, ids_stride, scores_stride, mm_stride, out_ids, out_scores, out_minmax);
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
+}
+}  // namespace
+}  // namespace crag
+
+extern "C" int crag_merge_topk(const float* scores, const int64_t* ids, const float* minmax, int parts, int nq,
+                               int k, int64_t* out_ids, float* out_scores, float* out_minmax,
+                               crag_stream_t stream) {
+  return crag::merge_pairs(scores, ids, minmax, int64_t(nq) * k * 8, int64_t(nq) * k * 4, int64_t(nq) * 2 * 4, parts, nq, k,
+                           out_ids, out_scores, out_minmax, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int crag_merge_topk_packed(const void* records, int64_t record_bytes, int parts, int nq, int k,
+                                      int64_t* out_ids, float* out_scores, float* out_minmax, crag_stream_t stream) {
+  const int64_t a = int64_t(nq) * k * 8, b = a + int64_t(nq) * k * 4, need = b + int64_t(nq) * 2 * 4;
+  if (record_bytes < need || record_bytes % 8) return crag::fail(CRAG_ERR_INVALID, "crag_merge_topk_packed: record_bytes %lld < %lld or not a multiple of 8", (long long)record_bytes, (long long)need);
+  if (!records && parts > 0) return crag::fail(CRAG_ERR_INVALID, "crag_merge_topk_packed: null pointer");
+  const char* base = static_cast<const char*>(records);
+  return crag::merge_pairs(reinterpret_cast<const float*>(base + a), reinterpret_cast<const int64_t*>(base),
+                           reinterpret_cast<const float*>(base + b), record_bytes, record_bytes, record_bytes, parts, nq, k,
+                           out_ids, out_scores, out_minmax, static_cast<cudaStream_t>(stream));
 }

@@ -24,18 +24,25 @@ def shard_bounds(n_rows: int, world: int) -> List[int]:
 
 def pack_partial(ids: torch.Tensor, scores: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:
     """(int64 [nq,k], fp32 [nq,k], fp32 [nq,2]) -> one contiguous uint8 buffer (a single collective payload)."""
-    return torch.cat([ids.contiguous().view(torch.uint8).reshape(-1), scores.contiguous().view(torch.uint8).reshape(-1),
-                      minmax.contiguous().view(torch.uint8).reshape(-1)])
+    from .index import packed_record_bytes, packed_views
+    nq, k = ids.shape
+    buf = torch.zeros(packed_record_bytes(nq, k), dtype=torch.uint8, device=ids.device)
+    v_ids, v_scores, v_mm = packed_views(buf, nq, k)
+    v_ids.copy_(ids)
+    v_scores.copy_(scores)
+    v_mm.copy_(minmax)
+    return buf
 
 
 def unpack_partials(buf: torch.Tensor, world: int, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """[world * bytes] uint8 -> ids int64 [world,nq,k], scores fp32 [world,nq,k], minmax fp32 [world,nq,2]."""
-    per = nq * k * 8 + nq * k * 4 + nq * 2 * 4
+    from .index import packed_record_bytes
+    per = packed_record_bytes(nq, k)
     b = buf.view(world, per)
     a, c = nq * k * 8, nq * k * 8 + nq * k * 4
     ids = b[:, :a].contiguous().view(torch.int64).view(world, nq, k)
     scores = b[:, a:c].contiguous().view(torch.float32).view(world, nq, k)
-    minmax = b[:, c:].contiguous().view(torch.float32).view(world, nq, 2)
+    minmax = b[:, c:c + nq * 8].contiguous().view(torch.float32).view(world, nq, 2)
     return ids, scores, minmax
 
 
@@ -63,14 +70,18 @@ class ShardedIndex:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
     def search_device(self, queries_bf16: torch.Tensor, k: int):
-        """Every rank passes the SAME query block; every rank returns the same global (ids, scores, minmax)."""
-        from .index import merge_topk
-        ids, scores, minmax = self.local.search_device(queries_bf16, k)
+        """Every rank passes the SAME query block; every rank returns the same global (ids, scores, minmax).
+
+        Per step: scan kernel + per-shard finalize kernel (writing straight into the packed send record) + ONE
+        all_gather_into_tensor + one merge kernel over the gathered records; no pack/unpack copies."""
+        from .index import merge_topk_packed, packed_record_bytes, packed_views
         if self.world == 1:
-            return ids, scores, minmax
+            return self.local.search_device(queries_bf16, k)
         nq = queries_bf16.shape[0]
-        mine = pack_partial(ids, scores, minmax)
-        gathered = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=mine.device)
+        per = packed_record_bytes(nq, k)
+        dev = queries_bf16.device
+        mine = torch.empty(per, dtype=torch.uint8, device=dev)
+        self.local.search_device(queries_bf16, k, out=packed_views(mine, nq, k))
+        gathered = torch.empty(self.world * per, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(gathered, mine, group=self.group)
-        g_ids, g_scores, g_mm = unpack_partials(gathered, self.world, nq, k)
-        return merge_topk(g_scores, g_ids, g_mm)
+        return merge_topk_packed(gathered, self.world, nq, k)

@@ -92,8 +92,9 @@ class DenseIndex:
             self._n = n1
 
     # ----------------------------------------------------------------- search
-    def search_device(self, queries: torch.Tensor, k: int,
-                      stream: Optional[torch.cuda.Stream] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    def search_device(self, queries: torch.Tensor, k: int, stream: Optional[torch.cuda.Stream] = None,
+                      out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Top-k of a device bf16 [nq, dim_pad] query block.
 
         Returns (ids int64 [nq, k], scores fp32 [nq, k], minmax fp32 [nq, 2]),
@@ -113,13 +114,17 @@ class DenseIndex:
         with torch.cuda.device(dev):
             st = stream if stream is not None else torch.cuda.current_stream(dev)
             with torch.cuda.stream(st):
-                ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-                scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
-                minmax = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+                if out is not None:
+                    ids, scores, minmax = out   # caller-provided (e.g. views of one packed send buffer)
+                else:
+                    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+                    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+                    minmax = torch.empty((nq, 2), dtype=torch.float32, device=dev)
                 ws_bytes = lib.crag_search_workspace_bytes(nq, k)
                 ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
                 rc = lib.crag_search_topk(
-                    self._buf.data_ptr() if self._n else 0, self._n, self.dim_pad, self._buf.stride(0) if self._buf.dim() == 2 and self._buf.shape[0] else self.dim_pad,
+                    self._buf.data_ptr() if self._n else 0, self._n, self.dim_pad,
+                    self._buf.stride(0) if self._buf.shape[0] else self.dim_pad,
                     self.row_offset, queries.data_ptr(), nq, k, ids.data_ptr(), scores.data_ptr(),
                     minmax.data_ptr(), ws.data_ptr(), ws_bytes, st.cuda_stream)
                 _native.check(rc, "crag_search_topk")
@@ -171,4 +176,33 @@ def merge_topk(scores: torch.Tensor, ids: torch.Tensor, minmax: Optional[torch.T
                                  out_ids.data_ptr(), out_scores.data_ptr(), _native.ptr(out_mm),
                                  torch.cuda.current_stream(dev).cuda_stream)
         _native.check(rc, "crag_merge_topk")
+    return out_ids, out_scores, out_mm
+
+
+def packed_record_bytes(nq: int, k: int) -> int:
+    """Bytes of one shard's packed (ids | scores | minmax) record (crag_merge_topk_packed layout)."""
+    return (nq * k * 8 + nq * k * 4 + nq * 2 * 4 + 15) // 16 * 16   # padded so consecutive records stay 8-byte aligned
+
+
+def packed_views(buf: torch.Tensor, nq: int, k: int):
+    """Three typed views (ids int64 [nq,k], scores fp32 [nq,k], minmax fp32 [nq,2]) of one uint8 record buffer."""
+    a, b = nq * k * 8, nq * k * 8 + nq * k * 4
+    return (buf[:a].view(torch.int64).view(nq, k), buf[a:b].view(torch.float32).view(nq, k),
+            buf[b:b + nq * 8].view(torch.float32).view(nq, 2))
+
+
+def merge_topk_packed(records: torch.Tensor, parts: int, nq: int, k: int):
+    """Merge `parts` packed records laid out back to back in one uint8 buffer (the all-gather output)."""
+    lib = _native.load()
+    dev = records.device
+    per = packed_record_bytes(nq, k)
+    if records.dtype != torch.uint8 or records.numel() < parts * per or not records.is_contiguous():
+        raise ValueError("records must be a contiguous uint8 buffer of parts * record bytes")
+    out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_mm = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.crag_merge_topk_packed(records.data_ptr(), per, parts, nq, k, out_ids.data_ptr(), out_scores.data_ptr(),
+                                        out_mm.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(rc, "crag_merge_topk_packed")
     return out_ids, out_scores, out_mm

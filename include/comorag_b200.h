@@ -112,6 +112,12 @@ CRAG_API int crag_search_finalize(const void* workspace, size_t workspace_bytes,
 CRAG_API int crag_merge_topk(const float* scores, const int64_t* ids, const float* minmax, int parts, int nq, int k,
                     int64_t* out_ids, float* out_scores, float* out_minmax, crag_stream_t stream);
 
+/* Same merge over PACKED per-shard records, the layout a single all-gather produces: record r (record_bytes apart,
+ * multiple of 8) = [ids int64 nq*k][scores fp32 nq*k][minmax fp32 nq*2].  Lets every rank write its
+ * crag_search_topk outputs as three views of one send buffer and merge the gathered buffer in place. */
+CRAG_API int crag_merge_topk_packed(const void* records, int64_t record_bytes, int parts, int nq, int k,
+                                    int64_t* out_ids, float* out_scores, float* out_minmax, crag_stream_t stream);
+
 /* ------------------------------------------------------------------ encoder
  * Dense projection of the encoder forward (BGEEmbedding.py:120 runs it through
  * HF's BertModel: attention.self.{query,key,value}, attention.output.dense,

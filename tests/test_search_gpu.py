@@ -188,3 +188,18 @@ def test_sharded_equals_unsharded_at_config2_scale(dev):
     want_i, want_s, want_mm, gaps = torch_reference_topk(corpus, queries, k)
     so.assert_topk_matches(ids.cpu().numpy(), scores.double().cpu().numpy(), want_i, want_s, gaps)
     np.testing.assert_allclose(mm.cpu().numpy(), want_mm, atol=1e-5)
+
+
+def test_packed_merge_equals_dense_merge(dev):
+    """crag_merge_topk_packed over all-gather-shaped records == crag_merge_topk over dense arrays."""
+    from comorag_b200.dist import pack_partial
+    from comorag_b200.index import merge_topk, merge_topk_packed
+    g = torch.Generator().manual_seed(3)
+    for world, nq, k in [(2, 3, 5), (8, 32, 10), (4, 7, 100)]:
+        scores = torch.randn(world, nq, k, generator=g).sort(dim=2, descending=True).values.to(dev)
+        ids = torch.randint(0, 1 << 40, (world, nq, k), generator=g).to(dev)
+        mm = torch.randn(world, nq, 2, generator=g).to(dev)
+        recs = torch.cat([pack_partial(ids[r], scores[r], mm[r]) for r in range(world)])
+        a = merge_topk_packed(recs, world, nq, k)
+        b = merge_topk(scores, ids, mm)
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
