@@ -45,6 +45,7 @@ struct SearchLayout {
            + kNQ * 8               // thr_key
            + kNQ * 4               // thr_f
            + kNQ * 4               // cnt
+           + kNQ * 8 + kNQ * 4     // continuation bound (key, score)
            + 4 * kNQ * 2 * 4       // min/max cross-warp reduction
            + 16;                   // tmem base
   }
@@ -56,8 +57,8 @@ struct SearchLayout {
 template <int KLIST, int CAP, int STAGES>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_constant__ CUtensorMap tm_q,
-                   int n_rows, int num_kb, int nq, int k, uint64_t* __restrict__ part_keys,
-                   float* __restrict__ part_minmax) {
+                   int n_rows, int num_kb, int nq, int k, const uint64_t* __restrict__ after_keys,
+                   uint64_t* __restrict__ part_keys, float* __restrict__ part_minmax) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -74,7 +75,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   float* thr_f = reinterpret_cast<float*>(thr_key + kNQ);  // [kNQ]
   int* cnt = reinterpret_cast<int*>(thr_f + kNQ);          // [kNQ]
   float* red = reinterpret_cast<float*>(cnt + kNQ);        // [4][kNQ][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red + 4 * kNQ * 2);
+  uint64_t* bnd_key = reinterpret_cast<uint64_t*>(red + 4 * kNQ * 2);  // [kNQ] admit only keys < bnd_key
+  float* bnd_f = reinterpret_cast<float*>(bnd_key + kNQ);              // [kNQ] score part of the bound
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bnd_f + kNQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,6 +108,10 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
     thr_key[threadIdx.x] = 0ull;
     thr_f[threadIdx.x] = -INFINITY;
     cnt[threadIdx.x] = 0;
+    // "search after": rank continuation for k > 128 -- only candidates strictly below the previous pass's last key
+    const uint64_t b = (after_keys != nullptr && int(threadIdx.x) < nq) ? after_keys[threadIdx.x] : ~0ull;
+    bnd_key[threadIdx.x] = b;
+    bnd_f[threadIdx.x] = (b == ~0ull) ? INFINITY : (b == 0ull ? -INFINITY : key_score(b));
   }
   tc_fence_before();
   __syncthreads();
@@ -189,7 +196,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
           const float s = __uint_as_float(r[q]);
           mn[q] = fminf(mn[q], s);
           mx[q] = fmaxf(mx[q], s);
-          if (s >= thr_f[q]) pending |= 1u << q;
+          if (s >= thr_f[q] && s <= bnd_f[q]) pending |= 1u << q;
         }
         if (nq < kNQ) pending &= (1u << nq) - 1u;
       }
@@ -197,6 +204,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
         bool want_flush = false;
 #pragma unroll
         for (int q = 0; q < kNQ; ++q) {
+          if (((pending >> q) & 1u) && make_key(__uint_as_float(r[q]), uint32_t(row)) >= bnd_key[q]) pending &= ~(1u << q);
           if ((pending >> q) & 1u) {
             const int slot = atomicAdd(&cnt[q], 1);
             if (slot < CAP) {
@@ -284,7 +292,8 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
                                                          int64_t ids_stride, int64_t scores_stride, int64_t mm_stride,
                                                          int64_t* __restrict__ out_ids,
                                                          float* __restrict__ out_scores,
-                                                         float* __restrict__ out_minmax) {
+                                                         float* __restrict__ out_minmax,
+                                                         uint64_t* __restrict__ last_keys) {
   constexpr int KPQ = KLIST + CAP;
   __shared__ uint64_t s_keys[4][KPQ];
   __shared__ uint64_t s_thr[4];
@@ -357,6 +366,7 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
     out_scores[size_t(q) * k + j] = s;
     out_ids[size_t(q) * k + j] = id;
   }
+  if (last_keys != nullptr && lane == 0) last_keys[q] = keys[k - 1];  // 0 when fewer than k rows qualified
   if (out_minmax != nullptr) {
     float a = INFINITY, b = -INFINITY;
     if (part_minmax != nullptr) {
@@ -399,12 +409,12 @@ SearchPlan plan_search(int k) {
 
 template <int KLIST, int CAP, int STAGES>
 int launch_search(const CUtensorMap& tm_corpus, const CUtensorMap& tm_q, int n_rows, int num_kb, int nq, int k,
-                  int grid, uint64_t* part_keys, float* part_minmax, cudaStream_t stream) {
+                  int grid, const uint64_t* after_keys, uint64_t* part_keys, float* part_minmax, cudaStream_t stream) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   const size_t smem = L::smem_bytes(num_kb);
   auto kern = search_topk_kernel<KLIST, CAP, STAGES>;
   CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, n_rows, num_kb, nq, k, part_keys, part_minmax);
+  kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, n_rows, num_kb, nq, k, after_keys, part_keys, part_minmax);
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }
@@ -444,7 +454,7 @@ inline int scan_grid(int64_t n_rows, const SearchPlan& plan) {
 
 // one corpus pass for <= 32 queries: per-CTA partial lists into the workspace
 int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride, const void* queries, int nq,
-              int k, void* workspace, const SearchPlan& plan, cudaStream_t stream) {
+              int k, const uint64_t* after_keys, void* workspace, const SearchPlan& plan, cudaStream_t stream) {
   const int grid = scan_grid(n_rows, plan);
   if (grid == 0) return CRAG_OK;
   uint64_t* part_keys = static_cast<uint64_t*>(workspace);
@@ -455,21 +465,21 @@ int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_st
   rc = make_tmap_bf16_2d(&tm_q, queries, uint64_t(nq), uint64_t(dim), uint64_t(dim) * 2, kNQ);
   if (rc != CRAG_OK) return rc;
   const int num_kb = dim / kBlockK;
-  if (k <= 64) return launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, part_keys, part_minmax, stream);
-  return launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, part_keys, part_minmax, stream);
+  if (k <= 64) return launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, part_keys, part_minmax, stream);
+  return launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, part_keys, part_minmax, stream);
 }
 
 // merge the per-CTA partials of one pass into the final (ids, scores, minmax) of its <= 32 queries
 int finalize_pass(const void* workspace, int64_t n_rows, int nq, int k, int64_t row_offset, int64_t* out_ids,
-                  float* out_scores, float* out_minmax, const SearchPlan& plan, cudaStream_t stream) {
+                  float* out_scores, float* out_minmax, uint64_t* last_keys, const SearchPlan& plan, cudaStream_t stream) {
   const int grid = scan_grid(n_rows, plan);
   const uint64_t* part_keys = static_cast<const uint64_t*>(workspace);
   const float* part_minmax = reinterpret_cast<const float*>(static_cast<const uint8_t*>(workspace) + plan.keys_bytes);
   const int mgrid = (nq + 3) / 4;
   if (k <= 64)
-    merge_topk_kernel<64, 64, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, 0, 0, 0, out_ids, out_scores, out_minmax);
+    merge_topk_kernel<64, 64, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, 0, 0, 0, out_ids, out_scores, out_minmax, last_keys);
   else
-    merge_topk_kernel<128, 128, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, 0, 0, 0, out_ids, out_scores, out_minmax);
+    merge_topk_kernel<128, 128, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, 0, 0, 0, out_ids, out_scores, out_minmax, last_keys);
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }
@@ -484,7 +494,7 @@ extern "C" int crag_search_scan(const void* corpus, int64_t n_rows, int dim, int
   int rc = check_search_args(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, workspace, workspace_bytes, plan);
   if (rc != CRAG_OK) return rc;
   if (nq > kNQ) return fail(CRAG_ERR_INVALID, "crag_search_scan handles one pass of at most %d queries (nq=%d)", kNQ, nq);
-  return scan_pass(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, workspace, plan, static_cast<cudaStream_t>(stream));
+  return scan_pass(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, nullptr, workspace, plan, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int crag_search_finalize(const void* workspace, size_t workspace_bytes, int64_t n_rows, int nq, int k,
@@ -494,13 +504,14 @@ extern "C" int crag_search_finalize(const void* workspace, size_t workspace_byte
   const SearchPlan plan = plan_search(k);
   if (!workspace || !out_ids || !out_scores) return fail(CRAG_ERR_INVALID, "crag_search_finalize: null pointer");
   if (workspace_bytes < plan.keys_bytes + plan.minmax_bytes) return fail(CRAG_ERR_WORKSPACE, "crag_search_finalize: workspace too small");
-  return finalize_pass(workspace, n_rows, nq, k, row_offset, out_ids, out_scores, out_minmax, plan, static_cast<cudaStream_t>(stream));
+  return finalize_pass(workspace, n_rows, nq, k, row_offset, out_ids, out_scores, out_minmax, nullptr, plan, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int crag_search_topk(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride,
-                                int64_t row_offset, const void* queries, int nq, int k, int64_t* out_ids,
-                                float* out_scores, float* out_minmax, void* workspace, size_t workspace_bytes,
-                                crag_stream_t stream_) {
+extern "C" int crag_search_topk_after(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride,
+                                      int64_t row_offset, const void* queries, int nq, int k,
+                                      const uint64_t* after_keys, int64_t* out_ids, float* out_scores,
+                                      float* out_minmax, uint64_t* last_keys, void* workspace,
+                                      size_t workspace_bytes, crag_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const SearchPlan plan = plan_search(k >= 1 && k <= 128 ? k : 1);
   int rc = check_search_args(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, workspace, workspace_bytes, plan);
@@ -508,13 +519,22 @@ extern "C" int crag_search_topk(const void* corpus, int64_t n_rows, int dim, int
   if (!out_ids || !out_scores) return fail(CRAG_ERR_INVALID, "search: null output pointer");
   for (int q0 = 0; q0 < nq; q0 += kNQ) {
     const int nqc = (nq - q0) < kNQ ? (nq - q0) : kNQ;
-    rc = scan_pass(corpus, n_rows, dim, corpus_row_stride, static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2, nqc, k, workspace, plan, stream);
+    rc = scan_pass(corpus, n_rows, dim, corpus_row_stride, static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2, nqc, k,
+                   after_keys ? after_keys + q0 : nullptr, workspace, plan, stream);
     if (rc != CRAG_OK) return rc;
     rc = finalize_pass(workspace, n_rows, nqc, k, row_offset, out_ids + size_t(q0) * k, out_scores + size_t(q0) * k,
-                       out_minmax ? out_minmax + size_t(q0) * 2 : nullptr, plan, stream);
+                       out_minmax ? out_minmax + size_t(q0) * 2 : nullptr, last_keys ? last_keys + q0 : nullptr, plan, stream);
     if (rc != CRAG_OK) return rc;
   }
   return CRAG_OK;
+}
+
+extern "C" int crag_search_topk(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride,
+                                int64_t row_offset, const void* queries, int nq, int k, int64_t* out_ids,
+                                float* out_scores, float* out_minmax, void* workspace, size_t workspace_bytes,
+                                crag_stream_t stream) {
+  return crag_search_topk_after(corpus, n_rows, dim, corpus_row_stride, row_offset, queries, nq, k, nullptr, out_ids,
+                                out_scores, out_minmax, nullptr, workspace, workspace_bytes, stream);
 }
 
 namespace crag {
@@ -527,9 +547,9 @@ int merge_pairs(const float* scores, const int64_t* ids, const float* minmax, in
   const int mgrid = (nq + 3) / 4;
   const float* mm = out_minmax ? minmax : nullptr;
   if (k <= 64)
-    merge_topk_kernel<64, 64, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, mm, parts, nq, nq, k, 0, ids_stride, scores_stride, mm_stride, out_ids, out_scores, out_minmax);
+    merge_topk_kernel<64, 64, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, mm, parts, nq, nq, k, 0, ids_stride, scores_stride, mm_stride, out_ids, out_scores, out_minmax, nullptr);
   else
-    merge_topk_kernel<128, 128, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, mm, parts, nq, nq, k, 0, ids_stride, scores_stride, mm_stride, out_ids, out_scores, out_minmax);
+    merge_topk_kernel<128, 128, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, mm, parts, nq, nq, k, 0, ids_stride, scores_stride, mm_stride, out_ids, out_scores, out_minmax, nullptr);
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }

@@ -102,8 +102,12 @@ class DenseIndex:
         Scores are raw inner products sorted descending (ties: ascending id);
         missing entries (n_rows < k) have id -1 / score -inf.
         """
-        if not (1 <= k <= MAX_K):
-            raise ValueError(f"k must be in [1, {MAX_K}]")
+        if k < 1:
+            raise ValueError("k must be >= 1")
+        if k > MAX_K:
+            if out is not None:
+                raise ValueError(f"out= is only supported for k <= {MAX_K}")
+            return self._search_device_paged(queries, k, stream)
         if queries.dtype != torch.bfloat16 or queries.dim() != 2 or queries.shape[1] != self.dim_pad:
             raise ValueError(f"queries must be bf16 [nq, {self.dim_pad}]")
         if not queries.is_contiguous():
@@ -128,6 +132,38 @@ class DenseIndex:
                     self.row_offset, queries.data_ptr(), nq, k, ids.data_ptr(), scores.data_ptr(),
                     minmax.data_ptr(), ws.data_ptr(), ws_bytes, st.cuda_stream)
                 _native.check(rc, "crag_search_topk")
+        return ids, scores, minmax
+
+    def _search_device_paged(self, queries: torch.Tensor, k: int, stream: Optional[torch.cuda.Stream]):
+        """k > 128: ceil(k/128) passes chained with crag_search_topk_after (exact rank continuation)."""
+        if queries.dtype != torch.bfloat16 or queries.dim() != 2 or queries.shape[1] != self.dim_pad:
+            raise ValueError(f"queries must be bf16 [nq, {self.dim_pad}]")
+        queries = queries.contiguous()
+        nq = queries.shape[0]
+        lib = _native.load()
+        dev = self.device
+        with torch.cuda.device(dev):
+            st = stream if stream is not None else torch.cuda.current_stream(dev)
+            with torch.cuda.stream(st):
+                ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+                scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+                minmax = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+                ws_bytes = lib.crag_search_workspace_bytes(nq, MAX_K)
+                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+                after = None
+                for p0 in range(0, k, MAX_K):
+                    kk = min(MAX_K, k - p0)
+                    p_ids = torch.empty((nq, kk), dtype=torch.int64, device=dev)
+                    p_sc = torch.empty((nq, kk), dtype=torch.float32, device=dev)
+                    last = torch.empty((nq,), dtype=torch.int64, device=dev)   # opaque u64 positions
+                    rc = lib.crag_search_topk_after(
+                        self._buf.data_ptr() if self._n else 0, self._n, self.dim_pad,
+                        self._buf.stride(0) if self._buf.shape[0] else self.dim_pad, self.row_offset,
+                        queries.data_ptr(), nq, kk, _native.ptr(after), p_ids.data_ptr(), p_sc.data_ptr(),
+                        minmax.data_ptr(), last.data_ptr(), ws.data_ptr(), ws_bytes, st.cuda_stream)
+                    _native.check(rc, "crag_search_topk_after")
+                    ids[:, p0:p0 + kk], scores[:, p0:p0 + kk] = p_ids, p_sc
+                    after = last
         return ids, scores, minmax
 
     def prepare_queries(self, queries) -> torch.Tensor:

@@ -36,7 +36,7 @@ def normalize_topk_scores(scores: np.ndarray, minmax: np.ndarray) -> np.ndarray:
 def dense_topk(index: DenseIndex, query_embeddings, k: int) -> Tuple[np.ndarray, np.ndarray]:
     """Batched dense_passage_retrieval truncated to the first k ranks: (ids int64 [nq, k], min-max-normalised
     scores fp32 [nq, k]) -- what tri_retrieve consumes at ComoRAG.py:499,516 (first qa_*_top_k ids)."""
-    ids, scores, minmax = index.search(query_embeddings, min(k, MAX_K))
+    ids, scores, minmax = index.search(query_embeddings, k)
     return ids, normalize_topk_scores(scores, minmax)
 
 
@@ -73,7 +73,34 @@ def get_similar_summaries(query: str, level_store, embedding_model, top_k: int =
         return [], []
     query_embedding = embedding_model.batch_encode(
         query, instruction='Given a question, retrieve relevant documents that best answer the question.', norm=True)
-    k = min(top_k, len(level_ids), MAX_K)
+    k = min(top_k, len(level_ids))
     ids, scores, minmax = level_store.search(query_embedding, k)
     norm = normalize_topk_scores(scores, minmax)[0]
     return [level_store.texts[i] for i in ids[0] if i >= 0], [float(s) for s, i in zip(norm, ids[0]) if i >= 0]
+
+
+def retrieve_knn(query_ids: List[str], key_ids: List[str], query_vecs, key_vecs, k: int = 2047,
+                 query_batch_size: int = 1000, key_batch_size: int = 10000, device=None):
+    """embed_utils.py:8-97: top-k most similar keys (cosine) for every query -> {query_id: (key ids, scores)}.
+
+    The reference L2-normalises both sides and does blocked torch.mm + torch.topk with a two-stage merge, i.e. the
+    exact top-min(k, #keys) per query, scores descending.  Here the normalised keys become a bf16 device shard and
+    the queries run through the fused kernel, 128 ranks per pass chained with crag_search_topk_after.  The two batch
+    size arguments are accepted for signature compatibility; blocking is the kernel's own.
+    """
+    import torch
+    if len(key_vecs) == 0:
+        return {}
+    q = torch.nn.functional.normalize(torch.as_tensor(np.asarray(query_vecs), dtype=torch.float32), dim=1)
+    kv = torch.nn.functional.normalize(torch.as_tensor(np.asarray(key_vecs), dtype=torch.float32), dim=1)
+    index = DenseIndex(kv.shape[1], device=device, capacity=kv.shape[0])
+    index.add(kv)
+    kk = min(int(k), kv.shape[0])
+    results = {}
+    step = 1024  # queries per launch group (32 per corpus pass inside the library)
+    for s0 in range(0, q.shape[0], step):
+        ids, scores, _ = index.search(q[s0:s0 + step], kk)
+        for i in range(ids.shape[0]):
+            valid = ids[i] >= 0
+            results[query_ids[s0 + i]] = ([key_ids[j] for j in ids[i][valid]], scores[i][valid].tolist())
+    return results

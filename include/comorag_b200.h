@@ -87,6 +87,16 @@ CRAG_API int crag_search_topk(const void* corpus, int64_t n_rows, int dim, int64
                      const void* queries, int nq, int k, int64_t* out_ids, float* out_scores, float* out_minmax,
                      void* workspace, size_t workspace_bytes, crag_stream_t stream);
 
+/* Rank continuation ("search after") for k > 128 -- e.g. the reference's retrieve_knn with k = 2047
+ * (embed_utils.py:8-97, ComoRAG.py:670-684).  after_keys[q] (device u64 [nq], or NULL for "from the top") is the
+ * opaque position returned in last_keys by the previous call for the same queries over the same shard; only rows
+ * ranking strictly after it are admitted, so ceil(K/128) calls return ranks [0,128), [128,256), ... exactly.
+ * last_keys[q] is 0 once the shard is exhausted (further calls return ids -1).  Positions are shard-local. */
+CRAG_API int crag_search_topk_after(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride,
+                                    int64_t row_offset, const void* queries, int nq, int k, const uint64_t* after_keys,
+                                    int64_t* out_ids, float* out_scores, float* out_minmax, uint64_t* last_keys,
+                                    void* workspace, size_t workspace_bytes, crag_stream_t stream);
+
 /* The two halves of crag_search_topk for ONE pass (nq <= 32), exported so a caller can time or overlap them:
  * crag_search_scan streams the shard once and leaves per-CTA partial lists in the workspace;
  * crag_search_finalize merges them into (ids, scores, minmax).  Same argument rules as crag_search_topk. */

@@ -203,3 +203,34 @@ def test_packed_merge_equals_dense_merge(dev):
         a = merge_topk_packed(recs, world, nq, k)
         b = merge_topk(scores, ids, mm)
         assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("n,dim,nq,k", [(5000, 128, 9, 300), (200, 64, 3, 500), (3000, 256, 33, 2047)])
+def test_rank_continuation_beyond_128(dev, n, dim, nq, k):
+    """k > 128 through chained crag_search_topk_after passes: exact ranks, no duplicates, -1 past the end."""
+    corpus, queries = make_unit_rows(n, dim, 300 + n), make_unit_rows(nq, dim, 400 + n)
+    want_i, want_s, want_mm, gaps = so.topk_exact(corpus.float().numpy(), queries.float().numpy(), k)
+    ids, scores, minmax = _index(corpus, dev).search(queries.float().numpy(), k)
+    so.assert_topk_matches(ids, scores.astype(np.float64), want_i, want_s, gaps, score_tol=1e-3)
+    for r in ids:
+        v = r[r >= 0]
+        assert len(set(v.tolist())) == len(v) == min(k, n)
+
+
+def test_retrieve_knn_matches_reference_golden(dev):
+    """retrieve_knn (embed_utils.py:8-97) on the fixture the reference itself produced (k=100, 300 x 2500 entities)."""
+    from comorag_b200.retrieval import retrieve_knn
+    gold = np.load(GOLD)
+    Q, K = gold["knn_Q"], gold["knn_K"]
+    res = retrieve_knn([f"q{i}" for i in range(len(Q))], [f"k{i}" for i in range(len(K))], Q, K, k=100, device=dev)
+    got_ids = np.array([[int(x[1:]) for x in res[f"q{i}"][0]] for i in range(len(Q))])
+    got_sc = np.array([res[f"q{i}"][1] for i in range(len(Q))], dtype=np.float64)
+    Kn = torch.nn.functional.normalize(torch.from_numpy(K), dim=1).bfloat16().float().numpy()   # what the shard stores
+    Qn = torch.nn.functional.normalize(torch.from_numpy(Q), dim=1).bfloat16().float().numpy()
+    want_i, want_s, _, gaps = so.topk_exact(Kn, Qn, 100)
+    so.assert_topk_matches(got_ids, got_sc, want_i, want_s, gaps, score_tol=1e-3)          # exact on quantised inputs
+    assert np.abs(got_sc - gold["knn_scores"]).max() < 4e-3                                 # bf16 storage vs reference fp32
+    overlap = np.mean([len(set(a) & set(b)) / 100 for a, b in zip(got_ids.tolist(), gold["knn_ids"].tolist())])
+    assert overlap > 0.97
+    big = retrieve_knn(["a"], [f"k{i}" for i in range(len(K))], Q[:1], K, k=2047, device=dev)   # reference default k
+    assert len(big["a"][0]) == 2047 and len(set(big["a"][0])) == 2047 and np.all(np.diff(big["a"][1]) <= 0)
