@@ -20,6 +20,7 @@ class EngineConfig:
     # engine-only knobs; defaults keep ComoRAG.py unchanged
     embedding_device: str = "cuda"
     embedding_token_budget: int = 16384                   # max packed tokens per encoder launch
+    embedding_store_append_only: bool = False             # raw append-only shards instead of per-upsert parquet rewrite
     embedding_coalesce: bool = False                      # batch concurrent callers' encodes/searches (coalescer.py)
     embedding_coalesce_wait_ms: float = 0.3
     embedding_coalesce_max_texts: int = 64

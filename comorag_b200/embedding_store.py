@@ -68,6 +68,11 @@ class EmbeddingStore:
         self._n = 0
         self._index = None  # DenseIndex, created on first use (needs a CUDA device)
         self._index_rows = 0
+        # persistence: "parquet" (reference behaviour: whole-file rewrite per upsert) or "append" (O(new rows) raw
+        # shards + jsonl; vdb_<ns>.parquet is produced on demand by export_parquet())
+        cfg = getattr(embedding_model, "global_config", None)
+        self._persist = "append" if getattr(cfg, "embedding_store_append_only", False) else "parquet"
+        self._base = os.path.join(db_filename, f"vdb_{self.namespace}")
         self._search_coalescer = None
         if getattr(getattr(embedding_model, "global_config", None), "embedding_coalesce", False):
             from .coalescer import CoalescedSearch
@@ -127,15 +132,83 @@ class EmbeddingStore:
             self._upsert(missing_ids, texts_to_encode, missing_embeddings)
 
     def _upsert(self, hash_ids, texts, embeddings):
+        n0 = self._n
         self._append_host(embeddings)
         self.hash_ids.extend(hash_ids)
         self.texts.extend(texts)
         logger.info("Saving new records.")
+        if self._persist == "append":
+            self._append_raw(n0)
+            self._rebuild_maps_incremental(n0)
+        else:
+            self._save_data()
+
+    # ---- append-only persistence: raw row shards + a jsonl row table
+    def _append_raw(self, n0: int) -> None:
+        import json
+        import torch
+        rows = self._host[n0:self._n]
+        with open(self._base + ".rows.jsonl", "a") as f:
+            for h, t in zip(self.hash_ids[n0:], self.texts[n0:]):
+                f.write(json.dumps({"hash_id": h, "content": t}) + "\n")
+        with open(self._base + ".f32", "ab") as f:
+            f.write(np.ascontiguousarray(rows, dtype=np.float32).tobytes())
+        dim_pad = (self._dim + 63) // 64 * 64
+        padded = torch.zeros((rows.shape[0], dim_pad), dtype=torch.bfloat16)
+        padded[:, : self._dim] = torch.from_numpy(np.ascontiguousarray(rows)).to(torch.bfloat16)
+        with open(self._base + ".bf16", "ab") as f:
+            f.write(padded.view(torch.int16).numpy().tobytes())
+        with open(self._base + ".meta.json", "w") as f:
+            json.dump({"dim": self._dim, "dim_pad": dim_pad, "rows": self._n, "format": "comorag_b200.raw.v1"}, f)
+
+    def _rebuild_maps_incremental(self, n0: int) -> None:
+        for i in range(n0, self._n):
+            h, t = self.hash_ids[i], self.texts[i]
+            self.hash_id_to_idx[h] = i
+            self.hash_id_to_row[h] = {"hash_id": h, "content": t}
+            self.hash_id_to_text[h] = t
+            self.text_to_hash_id[t] = h
+
+    def _load_raw(self) -> bool:
+        import json
+        meta_p = self._base + ".meta.json"
+        if not os.path.exists(meta_p):
+            return False
+        meta = json.load(open(meta_p))
+        rows = [json.loads(l) for l in open(self._base + ".rows.jsonl") if l.strip()]
+        n, d = meta["rows"], meta["dim"]
+        if len(rows) < n or os.path.getsize(self._base + ".f32") < n * d * 4:
+            raise ValueError(f"{self._base}: raw shard files are shorter than the {n} rows the meta file records")
+        self.hash_ids = [r["hash_id"] for r in rows[:n]]
+        self.texts = [r["content"] for r in rows[:n]]
+        self._dim = d
+        self._host = np.zeros((0, d), dtype=np.float32)
+        self._n = 0
+        if n:
+            self._append_host(np.fromfile(self._base + ".f32", dtype=np.float32, count=n * d).reshape(n, d))
+        self._rebuild_maps()
+        return True
+
+    def raw_shard_path(self) -> Optional[str]:
+        """Path of the bf16 [rows, dim_pad] shard file if it is in sync with the store (direct GPU upload)."""
+        p = self._base + ".bf16"
+        if self._persist == "append" and os.path.exists(p) and self._dim:
+            dim_pad = (self._dim + 63) // 64 * 64
+            if os.path.getsize(p) == self._n * dim_pad * 2:
+                return p
+        return None
+
+    def export_parquet(self) -> str:
+        """Write the reference-compatible vdb_<ns>.parquet (embedding_store.py:109-115) from the current rows."""
         self._save_data()
+        return self.filename
 
     # -------------------------------------------------------------- persistence
     def _load_data(self):
         """embedding_store.py:92-107."""
+        if self._persist == "append" and self._load_raw():
+            logger.info(f"Loaded {len(self.hash_ids)} records from {self._base}.* (raw shards)")
+            return
         if os.path.exists(self.filename):
             import pyarrow.parquet as pq
             table = pq.read_table(self.filename)
@@ -215,6 +288,10 @@ class EmbeddingStore:
                 device = getattr(self.embedding_model, "device", None)
                 self._index = DenseIndex(self._dim, device=device, capacity=max(self._n, 1024))
                 self._index_rows = 0
+                shard = self.raw_shard_path()
+                if shard is not None and self._n:
+                    self._index.add_bf16_file(shard, self._n)   # bf16 rows straight from disk, no fp32 round trip
+                    self._index_rows = self._n
             if self._index_rows < self._n:
                 self._index.add(self._host[self._index_rows: self._n])
                 self._index_rows = self._n

@@ -91,6 +91,34 @@ class DenseIndex:
             self._buf[n0:n1, : self.dim] = v.to(self.device, non_blocking=True).to(torch.bfloat16)
             self._n = n1
 
+    def add_bf16_file(self, path: str, n_rows: int) -> None:
+        """Append n_rows raw bf16 [*, dim_pad] rows from a file written by EmbeddingStore's append-only persistence."""
+        raw = np.fromfile(path, dtype=np.int16, count=n_rows * self.dim_pad)
+        if raw.size != n_rows * self.dim_pad:
+            raise ValueError(f"{path}: expected {n_rows} rows of {self.dim_pad} bf16")
+        rows = torch.from_numpy(raw).view(torch.bfloat16).view(n_rows, self.dim_pad)
+        with self._lock:
+            n0, n1 = self._n, self._n + n_rows
+            self._reserve(n1)
+            self._buf[n0:n1] = rows.to(self.device, non_blocking=True)
+            self._n = n1
+
+    def save(self, path: str) -> None:
+        """Raw bf16 [n_rows, dim_pad] dump + json meta (per-rank shard file for a sharded index)."""
+        import json
+        self._buf[: self._n].cpu().view(torch.int16).numpy().tofile(path)
+        with open(path + ".meta.json", "w") as f:
+            json.dump({"dim": self.dim, "dim_pad": self.dim_pad, "rows": self._n, "row_offset": self.row_offset,
+                       "format": "comorag_b200.raw.v1"}, f)
+
+    @classmethod
+    def load(cls, path: str, device: Optional[torch.device] = None) -> "DenseIndex":
+        import json
+        meta = json.load(open(path + ".meta.json"))
+        self = cls(meta["dim"], device=device, capacity=meta["rows"], row_offset=meta.get("row_offset", 0))
+        self.add_bf16_file(path, meta["rows"])
+        return self
+
     # ----------------------------------------------------------------- search
     def search_device(self, queries: torch.Tensor, k: int, stream: Optional[torch.cuda.Stream] = None,
                       out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None

@@ -90,3 +90,29 @@ def test_id_scheme_and_in_call_dedup(tmp_path):
     s = EmbeddingStore(M(), str(tmp_path / "x"), 2, "entity")
     s.insert_strings(["a", "b", "a"])          # duplicate inside one call collapses (dict keyed by id)
     assert s.texts == ["a", "b"] and len(s.embeddings) == 2
+
+
+def test_append_only_persistence_roundtrip(gold, tmp_path):
+    """Opt-in O(new rows) persistence: raw fp32/bf16 shards + jsonl; same lookups after reload; parquet on demand."""
+    import types
+    import torch
+    model = ReplayModel(gold)
+    model.global_config = types.SimpleNamespace(embedding_store_append_only=True)
+    d = str(tmp_path / "chunk_embeddings")
+    store = EmbeddingStore(model, d, 4, "chunk")
+    store.insert_strings(gold["texts"][:4])
+    store.insert_strings(gold["texts"][2:])            # appends only the 3 new rows
+    assert not os.path.exists(store.filename)          # no parquet rewrite happened
+    assert store.get_all_ids() == gold["hash_ids"]
+    again = EmbeddingStore(model, d, 4, "chunk")
+    assert again.get_all_ids() == gold["hash_ids"] and again.texts == gold["texts"]
+    np.testing.assert_array_equal(again.get_embeddings(again.hash_ids), gold["embeddings"])
+    assert again.text_to_hash_id[gold["texts"][3]] == gold["hash_ids"][3]
+    shard = again.raw_shard_path()
+    raw = torch.from_numpy(np.fromfile(shard, dtype=np.int16)).view(torch.bfloat16).view(7, 128)
+    assert torch.equal(raw, torch.from_numpy(gold["embeddings"]).bfloat16())
+    import pyarrow.parquet as pq
+    schema = pq.read_schema(again.export_parquet())
+    assert {n: str(schema.field(n).type) for n in schema.names} == gold["parquet_schema"]
+    ref_style = EmbeddingStore(ReplayModel(gold), d, 4, "chunk")       # a parquet-mode store reads the export
+    assert ref_style.get_all_ids() == gold["hash_ids"]
