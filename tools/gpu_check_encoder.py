@@ -20,6 +20,7 @@ GEMM_CASES = [  # M, N, K, epi, variant (0 = default dispatch: CTA-pair kernel w
     (16384, 3072, 1024, 0, 0), (16384, 3072, 1024, 0, 1), (16384, 1024, 1024, 2, 0), (16384, 1024, 1024, 2, 1),
     (16384, 4096, 1024, 1, 0), (16384, 4096, 1024, 1, 1), (16384, 1024, 4096, 2, 0), (16384, 1024, 4096, 2, 1),
     (16384, 1152, 384, 0, 0), (16384, 384, 1536, 2, 0), (16384, 768, 3072, 2, 0),
+    (16384, 1024, 1024, 2, 2), (16384, 1024, 4096, 2, 2), (16384, 3072, 1024, 0, 2), (16384, 768, 768, 2, 0), (16384, 768, 768, 2, 2),
 ]
 ATTN_CASES = [  # H, heads, lengths
     (128, 4, [5, 64, 65, 1, 130]), (1024, 16, [512, 33, 200, 512]), (384, 12, [77, 512, 300]), (768, 12, [128] * 6),
