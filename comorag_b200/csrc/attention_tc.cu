@@ -1,0 +1,290 @@
+// K2 on tcgen05: varlen multi-head self-attention for head dim 64 (BERT/BGE base & large).
+//
+//   ctx = softmax(Q K^T / sqrt(dh)) V      per (sequence, head), keys restricted to the sequence
+//
+// One CTA per (sequence, head, 128-query tile), two CTAs co-resident per SM so one CTA's softmax (MUFU-bound:
+// 128 x L exp2 per tile) overlaps the other's TMA + MMA.  192 threads:
+//   warp 0   TMA: Q tile once, then K_j / V_j blocks of 128 keys through a 2-stage ring (boxes 128 rows x 64 cols,
+//            128-byte swizzle, straight out of the packed [T, 3H] qkv activation)
+//   warp 1   tcgen05.mma: S = Q K_j^T (M=128, N=128, K=64) into TMEM columns [0,128);
+//            O += P_j V_j (M=128, N=64, K=128; V is consumed MN-major, i.e. as stored) into columns [128,192)
+//   warps 2-5  softmax: thread = query row (one TMEM lane): tcgen05.ld the 128 scores twice (max pass, exp pass),
+//            online max/sum in registers, P_j written to smem in the UMMA K-major 128B-swizzle layout, O rescaled
+//            in TMEM (tcgen05.ld / .st) when the running max moved, final O / l -> bf16 -> ctx.
+// MMAs retire in issue order, so "S_j is ready" also means "P_{j-1} V_{j-1} has landed in O".
+#include "common.cuh"
+#include "encoder.cuh"
+#include "ptx.cuh"
+
+namespace crag {
+
+constexpr int kAttBM = 128;   // queries per CTA
+constexpr int kAttBN = 128;   // keys per block
+constexpr int kAttDH = 64;
+constexpr int kAttThreads = 192;
+constexpr uint32_t kAttTmemCols = 256;  // S: [0,128), O: [128,192)
+constexpr int kAttTileBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
+// smem: Q 16K | K 16K | V0 16K | V1 16K | P 32K | barriers  (~97 KB: two CTAs per SM)
+constexpr size_t kAttSmemBytes = 1024 + 4 * kAttTileBytes + 2 * kAttTileBytes + 128;
+
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float att_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Shared-memory descriptor for an MN-major operand stored as [K rows][64 MN elements = 128 B] with the 128-byte
+// swizzle (a TMA box of a row-major [keys, d] matrix): 8-row (K) groups are 1024 B apart (SBO); there is a single
+// 64-element MN block, so LBO is unused.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_bmn(uint32_t M, uint32_t N) {
+  return umma_idesc_bf16_f32(M, N) | (1u << 16);  // b_major = MN
+}
+
+__global__ void __launch_bounds__(kAttThreads, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* __restrict__ cu_seqlens, int H,
+                    float scale_log2e, __nv_bfloat16* __restrict__ ctx) {
+  const int seq = blockIdx.z, head = blockIdx.y;
+  const int start = __ldg(cu_seqlens + seq);
+  const int L = __ldg(cu_seqlens + seq + 1) - start;
+  const int q0 = blockIdx.x * kAttBM;
+  if (q0 >= L) return;
+  const int n_blk = (L + kAttBN - 1) / kAttBN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kAttTileBytes;            // single buffer: K_j is dead once S_j has been issued and retired
+  uint8_t* sV = sK + kAttTileBytes;            // [2]
+  uint8_t* sP = sV + 2 * kAttTileBytes;        // 2 x 16 KB: keys [0,64) and [64,128) of the block
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + 2 * kAttTileBytes);
+  uint64_t* bar_k_full = bar_q + 1;
+  uint64_t* bar_k_empty = bar_k_full + 1;
+  uint64_t* bar_v_full = bar_k_empty + 1;      // [2]
+  uint64_t* bar_v_empty = bar_v_full + 2;      // [2]
+  uint64_t* bar_s = bar_v_empty + 2;           // S_j ready (and P_{j-1} V_{j-1} retired)
+  uint64_t* bar_p = bar_s + 1;                 // P_j written (and S_j consumed)
+  uint64_t* bar_o = bar_p + 1;                 // final O ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_k_full, 1);
+    mbar_init(bar_k_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_v_full[s], 1);
+      mbar_init(&bar_v_empty[s], 1);
+    }
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 4);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kAttTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const int row0 = start + q0;
+      mbar_arrive_expect_tx(bar_q, kAttTileBytes);
+      tma_load_2d(&tm_qkv, bar_q, sQ, head * kAttDH, row0);
+      for (int j = 0; j < n_blk; ++j) {
+        const int st = j & 1;
+        // V_j's stage frees (P_{j-2} V_{j-2} retired) before K's buffer does (S_{j-1} retired): load V first
+        mbar_wait(&bar_v_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bar_v_full[st], kAttTileBytes);
+        tma_load_2d(&tm_qkv, &bar_v_full[st], sV + st * kAttTileBytes, 2 * H + head * kAttDH, start + j * kAttBN);
+        mbar_wait(bar_k_empty, (j & 1) ^ 1);
+        mbar_arrive_expect_tx(bar_k_full, kAttTileBytes);
+        tma_load_2d(&tm_qkv, bar_k_full, sK, H + head * kAttDH, start + j * kAttBN);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(kAttBM, kAttBN);
+      constexpr uint32_t idesc_o = umma_idesc_bf16_f32_bmn(kAttBM, kAttDH);
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      mbar_wait(bar_q, 0);
+      for (int j = 0; j <= n_blk; ++j) {
+        if (j > 0) {
+          // O (+)= P_{j-1} V_{j-1}: 2 sub-tiles of 64 keys x 4 k-steps of 16 keys
+          const int st = (j - 1) & 1;
+          mbar_wait(&bar_v_full[st], ((j - 1) >> 1) & 1);
+          mbar_wait(bar_p, (j - 1) & 1);
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(sV + st * kAttTileBytes);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t a_desc = umma_desc_k_sw128(p_addr + (kk >> 2) * kAttTileBytes + (kk & 3) * 32);
+            const uint64_t b_desc = umma_desc_mn_sw128(v_addr + kk * 16 * 128);
+            umma_f16(tmem_o, a_desc, b_desc, idesc_o, (j > 1 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&bar_v_empty[st]);
+          if (j == n_blk) { umma_commit(bar_o); break; }
+        }
+        mbar_wait(bar_k_full, j & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK);
+#pragma unroll
+        for (int ks = 0; ks < kAttDH / 16; ++ks)
+          umma_f16(tmem_s, umma_desc_k_sw128(q_addr + ks * 32), umma_desc_k_sw128(k_addr + ks * 32), idesc_s, ks > 0);
+        umma_commit(bar_k_empty);
+        umma_commit(bar_s);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* p_row = sP + r * 128;
+    const int swz = r & 7;
+    for (int j = 0; j < n_blk; ++j) {
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+      const int kbase = j * kAttBN;
+      const bool ragged = kbase + kAttBN > L;
+      // pass 1: block max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(v[i]);
+          if (ragged && kbase + c * 32 + i >= L) s = -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * scale_log2e);   // finite: every block has >= 1 valid key
+      const float alpha = att_exp2(m_run - m_new);
+      // pass 2: p = exp2(s*scale - m), row sum, bf16 P into the swizzled K-major tile
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
+          float p0 = att_exp2(fmaf(s0, scale_log2e, -m_new)), p1 = att_exp2(fmaf(s1, scale_log2e, -m_new));
+          if (ragged) {
+            if (kbase + c * 32 + 2 * i >= L) p0 = 0.f;
+            if (kbase + c * 32 + 2 * i + 1 >= L) p1 = 0.f;
+          }
+          rs += p0 + p1;
+          __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+          packed[i] = *reinterpret_cast<uint32_t*>(&b);
+        }
+        // 32 keys = 4 x 16-byte chunks; chunk index within the 64-key sub-tile: (c & 1) * 4 + q
+        uint8_t* sub = p_row + (c >> 1) * kAttTileBytes;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(sub + ((chunk ^ swz) * 16)) =
+              make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
+      }
+      l_run = l_run * alpha + rs;
+      m_run = m_new;
+      // rescale the running O (P_{j-1} V_{j-1} has retired: S_j's commit covers it)
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_o + lane_addr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_32x32b_x32(tmem_o + lane_addr + c * 32, v);
+        }
+        tmem_st_wait();
+      }
+      fence_proxy_async();   // P (generic-proxy stores) -> visible to the tensor core's async proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+    }
+    // epilogue: O / l -> bf16 -> ctx[start + q0 + r, head*64 .. +64)
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    const int row = q0 + r;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_o + lane_addr + c * 32, v);
+      tmem_ld_wait();
+      if (row < L) {
+        __nv_bfloat16* dst = ctx + int64_t(start + row) * H + head * kAttDH + c * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 2 * i]) * inv,
+                                                     __uint_as_float(v[q * 8 + 2 * i + 1]) * inv);
+            o[i] = *reinterpret_cast<uint32_t*>(&b);
+          }
+          *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kAttTmemCols);
+}
+
+int launch_attention_tc(const void* qkv, const int32_t* cu_seqlens, int n_seqs, int total_tokens, int max_len, int H,
+                        int heads, void* ctx, cudaStream_t stream) {
+  if (n_seqs <= 0 || max_len <= 0 || total_tokens <= 0) return CRAG_OK;
+  if (H / heads != kAttDH) return fail(CRAG_ERR_UNSUPPORTED, "attention_tc: head dim must be 64");
+  CUtensorMap tm;
+  int rc = make_tmap_bf16_2d(&tm, qkv, uint64_t(total_tokens), uint64_t(3) * H, uint64_t(3) * H * 2, 128);
+  if (rc != CRAG_OK) return rc;
+  CRAG_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAttSmemBytes)));
+  const dim3 grid((max_len + kAttBM - 1) / kAttBM, heads, n_seqs);
+  const float scale_log2e = 1.4426950408889634f / sqrtf(float(kAttDH));
+  attention_tc_kernel<<<grid, kAttThreads, kAttSmemBytes, stream>>>(tm, cu_seqlens, H, scale_log2e,
+                                                                    static_cast<__nv_bfloat16*>(ctx));
+  CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
+}
+
+}  // namespace crag

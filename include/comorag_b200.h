@@ -225,6 +225,11 @@ CRAG_API int crag_pool_normalize(const void* hidden, const int32_t* cu_seqlens, 
 CRAG_API int crag_attention_varlen(const void* qkv, const int32_t* cu_seqlens, int n_seqs, int max_seqlen,
                                    int hidden_size, int heads, void* ctx, crag_stream_t stream);
 
+/* The same attention on the tcgen05 tensor cores (head dim 64 only): S = Q K^T and O += P V as UMMA tiles with TMEM
+ * accumulators, Q/K/V staged by TMA.  total_tokens = rows of qkv (sizes the TMA tensor map). */
+CRAG_API int crag_attention_varlen_tc(const void* qkv, const int32_t* cu_seqlens, int n_seqs, int total_tokens,
+                                      int max_seqlen, int hidden_size, int heads, void* ctx, crag_stream_t stream);
+
 /* torch.nn.LayerNorm over the last dimension, bf16 in/out, fp32 statistics
  * (BertSelfOutput / BertOutput LayerNorm). hidden_size <= 1024, multiple of 8. */
 CRAG_API int crag_layernorm(const void* in, int rows, int hidden_size, const float* gamma, const float* beta,

@@ -22,8 +22,10 @@ GEMM_CASES = [  # M, N, K, epi, variant (0 = default dispatch: CTA-pair kernel w
     (16384, 1152, 384, 0, 0), (16384, 384, 1536, 2, 0), (16384, 768, 3072, 2, 0),
     (16384, 1024, 1024, 2, 2), (16384, 1024, 4096, 2, 2), (16384, 3072, 1024, 0, 2), (16384, 768, 768, 2, 0), (16384, 768, 768, 2, 2),
 ]
-ATTN_CASES = [  # H, heads, lengths
-    (128, 4, [5, 64, 65, 1, 130]), (1024, 16, [512, 33, 200, 512]), (384, 12, [77, 512, 300]), (768, 12, [128] * 6),
+ATTN_CASES = [  # H, heads, lengths, tc (1 = tcgen05 kernel)
+    (128, 4, [5, 64, 65, 1, 130], 0), (1024, 16, [512, 33, 200, 512], 0), (384, 12, [77, 512, 300], 0), (768, 12, [128] * 6, 0),
+    (128, 2, [5, 64, 65, 1, 130, 128, 129, 300], 1), (1024, 16, [512, 33, 200, 512], 1), (768, 12, [128] * 6, 1),
+    (1024, 16, [512] * 32, 0), (1024, 16, [512] * 32, 1),
 ]
 ENC_CASES = [  # name, cfg args, lengths, std
     ("tiny", (128, 2, 4, 256, 1000), [5, 64, 65, 1, 130, 17], 0.02),
@@ -81,7 +83,7 @@ def attn_case(i):
     import torch
     from comorag_b200 import _native
     lib = _native.load()
-    H, heads, lens = ATTN_CASES[i]
+    H, heads, lens, tc = ATTN_CASES[i]
     dh = H // heads
     dev = torch.device("cuda:0")
     T = sum(lens)
@@ -89,9 +91,15 @@ def attn_case(i):
     qkv = (torch.randn(T, 3 * H, generator=g, device=dev)).bfloat16()
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
     ctx = torch.zeros(T, H, dtype=torch.bfloat16, device=dev)
-    rc = lib.crag_attention_varlen(qkv.data_ptr(), cu.data_ptr(), len(lens), max(lens), H, heads, ctx.data_ptr(),
-                                   torch.cuda.current_stream().cuda_stream)
-    _native.check(rc, "crag_attention_varlen")
+    def run():
+        if tc:
+            rc = lib.crag_attention_varlen_tc(qkv.data_ptr(), cu.data_ptr(), len(lens), T, max(lens), H, heads, ctx.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream)
+        else:
+            rc = lib.crag_attention_varlen(qkv.data_ptr(), cu.data_ptr(), len(lens), max(lens), H, heads, ctx.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream)
+        _native.check(rc, "crag_attention_varlen")
+    run()
     torch.cuda.synchronize()
     ref = torch.zeros(T, H, device=dev)
     s = 0
@@ -102,7 +110,19 @@ def attn_case(i):
         ref[s:s + L] = (att @ v).transpose(0, 1).reshape(L, H)
         s += L
     err = (ctx.float() - ref).abs()
-    return {"kind": "attn", "shape": [H, heads, lens], "max_err": float(err.max()), "ok": bool(err.max() < 0.03)}
+    res = {"kind": "attn", "tc": tc, "shape": [H, heads, lens[:8], len(lens)], "max_err": float(err.max()), "ok": bool(err.max() < 0.03)}
+    if T >= 8192:
+        for _ in range(3):
+            run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        res.update(ms=ms, tflops=sum(4.0 * L * L * dh * heads for L in lens) / ms / 1e9)
+    return res
 
 
 def ln_case(i):
