@@ -174,38 +174,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* _
       tc_fence_after();
       const int kbase = j * kAttBN;
       const bool ragged = kbase + kAttBN > L;
-      // pass 1: block max
+      // all 128 scores of the row in registers: four tcgen05.ld in flight, one wait
+      uint32_t v[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_s + lane_addr + c * 32, v[c]);
+      tmem_ld_wait();
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_addr + c * 32, v);
-        tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
+          float s = __uint_as_float(v[c][i]);
           if (ragged && kbase + c * 32 + i >= L) s = -INFINITY;
+          v[c][i] = __float_as_uint(s);
           mx = fmaxf(mx, s);
         }
-      }
       const float m_new = fmaxf(m_run, mx * scale_log2e);   // finite: every block has >= 1 valid key
       const float alpha = att_exp2(m_run - m_new);
-      // pass 2: p = exp2(s*scale - m), row sum, bf16 P into the swizzled K-major tile
+      // p = exp2(s*scale - m) (masked keys: exp2(-inf) = 0), row sum, bf16 P into the swizzled K-major tile
       float rs = 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_addr + c * 32, v);
-        tmem_ld_wait();
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
-          float p0 = att_exp2(fmaf(s0, scale_log2e, -m_new)), p1 = att_exp2(fmaf(s1, scale_log2e, -m_new));
-          if (ragged) {
-            if (kbase + c * 32 + 2 * i >= L) p0 = 0.f;
-            if (kbase + c * 32 + 2 * i + 1 >= L) p1 = 0.f;
-          }
+          const float p0 = att_exp2(fmaf(__uint_as_float(v[c][2 * i]), scale_log2e, -m_new));
+          const float p1 = att_exp2(fmaf(__uint_as_float(v[c][2 * i + 1]), scale_log2e, -m_new));
           rs += p0 + p1;
           __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
           packed[i] = *reinterpret_cast<uint32_t*>(&b);
