@@ -179,16 +179,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* _
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_s + lane_addr + c * 32, v[c]);
       tmem_ld_wait();
+      if (ragged) {  // only the last block of a sequence whose length is not a multiple of 128
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kbase + c * 32 + i >= L) v[c][i] = 0xff800000u;  // -inf: exp2 -> 0, never the max
+      }
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[c][i]);
-          if (ragged && kbase + c * 32 + i >= L) s = -INFINITY;
-          v[c][i] = __float_as_uint(s);
-          mx = fmaxf(mx, s);
-        }
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[c][i]));
       const float m_new = fmaxf(m_run, mx * scale_log2e);   // finite: every block has >= 1 valid key
       const float alpha = att_exp2(m_run - m_new);
       // p = exp2(s*scale - m) (masked keys: exp2(-inf) = 0), row sum, bf16 P into the swizzled K-major tile
