@@ -19,13 +19,19 @@
 namespace crag {
 
 constexpr int kAttBM = 128;   // queries per CTA
-constexpr int kAttBN = 128;   // keys per block
 constexpr int kAttDH = 64;
 constexpr int kAttThreads = 192;
-constexpr uint32_t kAttTmemCols = 256;  // S: [0,128), O: [128,192)
-constexpr int kAttTileBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
-// smem: Q 16K | K 16K | V0 16K | V1 16K | P 32K | barriers  (~97 KB: two CTAs per SM)
-constexpr size_t kAttSmemBytes = 1024 + 4 * kAttTileBytes + 2 * kAttTileBytes + 128;
+constexpr int kAttTileBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16 (Q tile; one 64-key sub-tile of P)
+// BN = keys per block.  BN = 64: S 64 + O 64 TMEM columns and ~57 KB smem -> three CTAs per SM;
+// BN = 128: S 128 + O 64 columns (256 allocated), ~97 KB -> two CTAs per SM.
+template <int BN>
+struct AttCfg {
+  static constexpr int kKVBytes = BN * 64 * 2;                 // one K or V block
+  static constexpr int kPBytes = 128 * BN * 2;                 // P: BN/64 sub-tiles of 16 KB
+  static constexpr uint32_t kTmemCols = BN == 64 ? 128 : 256;  // S: [0,BN), O: [BN, BN+64)
+  static constexpr int kMinCtas = BN == 64 ? 3 : 2;
+  static constexpr size_t smem_bytes() { return 1024 + kAttTileBytes + 3 * kKVBytes + kPBytes + 128; }
+};
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -62,9 +68,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_bmn(uint32_t M, uint3
   return umma_idesc_bf16_f32(M, N) | (1u << 16);  // b_major = MN
 }
 
-__global__ void __launch_bounds__(kAttThreads, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* __restrict__ cu_seqlens, int H,
-                    float scale_log2e, __nv_bfloat16* __restrict__ ctx) {
+template <int BN>
+__global__ void __launch_bounds__(kAttThreads, AttCfg<BN>::kMinCtas)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                    const int32_t* __restrict__ cu_seqlens, int H, float scale_log2e, __nv_bfloat16* __restrict__ ctx) {
+  using C = AttCfg<BN>;
+  constexpr int kAttBN = BN;
+  constexpr int NC = BN / 32;  // 32-column TMEM load chunks per score row
   const int seq = blockIdx.z, head = blockIdx.y;
   const int start = __ldg(cu_seqlens + seq);
   const int L = __ldg(cu_seqlens + seq + 1) - start;
@@ -76,9 +86,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* _
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kAttTileBytes;            // single buffer: K_j is dead once S_j has been issued and retired
-  uint8_t* sV = sK + kAttTileBytes;            // [2]
-  uint8_t* sP = sV + 2 * kAttTileBytes;        // 2 x 16 KB: keys [0,64) and [64,128) of the block
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + 2 * kAttTileBytes);
+  uint8_t* sV = sK + C::kKVBytes;              // [2]
+  uint8_t* sP = sV + 2 * C::kKVBytes;          // BN/64 sub-tiles of 16 KB (64 keys each)
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + C::kPBytes);
   uint64_t* bar_k_full = bar_q + 1;
   uint64_t* bar_k_empty = bar_k_full + 1;
   uint64_t* bar_v_full = bar_k_empty + 1;      // [2]
@@ -90,7 +100,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* _
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
     mbar_init(bar_q, 1);
     mbar_init(bar_k_full, 1);
     mbar_init(bar_k_empty, 1);
@@ -104,47 +115,47 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* _
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kAttTmemCols);
+    tmem_alloc(tmem_slot, C::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + BN;
 
   if (warp == 0) {
     if (elect_one()) {
       const int row0 = start + q0;
       mbar_arrive_expect_tx(bar_q, kAttTileBytes);
-      tma_load_2d(&tm_qkv, bar_q, sQ, head * kAttDH, row0);
+      tma_load_2d(&tm_q, bar_q, sQ, head * kAttDH, row0);
       for (int j = 0; j < n_blk; ++j) {
         const int st = j & 1;
         // V_j's stage frees (P_{j-2} V_{j-2} retired) before K's buffer does (S_{j-1} retired): load V first
         mbar_wait(&bar_v_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&bar_v_full[st], kAttTileBytes);
-        tma_load_2d(&tm_qkv, &bar_v_full[st], sV + st * kAttTileBytes, 2 * H + head * kAttDH, start + j * kAttBN);
+        mbar_arrive_expect_tx(&bar_v_full[st], C::kKVBytes);
+        tma_load_2d(&tm_kv, &bar_v_full[st], sV + st * C::kKVBytes, 2 * H + head * kAttDH, start + j * kAttBN);
         mbar_wait(bar_k_empty, (j & 1) ^ 1);
-        mbar_arrive_expect_tx(bar_k_full, kAttTileBytes);
-        tma_load_2d(&tm_qkv, bar_k_full, sK, H + head * kAttDH, start + j * kAttBN);
+        mbar_arrive_expect_tx(bar_k_full, C::kKVBytes);
+        tma_load_2d(&tm_kv, bar_k_full, sK, H + head * kAttDH, start + j * kAttBN);
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(kAttBM, kAttBN);
+      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(kAttBM, BN);
       constexpr uint32_t idesc_o = umma_idesc_bf16_f32_bmn(kAttBM, kAttDH);
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
       mbar_wait(bar_q, 0);
       for (int j = 0; j <= n_blk; ++j) {
         if (j > 0) {
-          // O (+)= P_{j-1} V_{j-1}: 2 sub-tiles of 64 keys x 4 k-steps of 16 keys
+          // O (+)= P_{j-1} V_{j-1}: BN/64 sub-tiles of 64 keys x 4 k-steps of 16 keys
           const int st = (j - 1) & 1;
           mbar_wait(&bar_v_full[st], ((j - 1) >> 1) & 1);
           mbar_wait(bar_p, (j - 1) & 1);
           tc_fence_after();
-          const uint32_t v_addr = smem_u32(sV + st * kAttTileBytes);
+          const uint32_t v_addr = smem_u32(sV + st * C::kKVBytes);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
+          for (int kk = 0; kk < BN / 16; ++kk) {
             const uint64_t a_desc = umma_desc_k_sw128(p_addr + (kk >> 2) * kAttTileBytes + (kk & 3) * 32);
             const uint64_t b_desc = umma_desc_mn_sw128(v_addr + kk * 16 * 128);
             umma_f16(tmem_o, a_desc, b_desc, idesc_o, (j > 1 || kk > 0) ? 1u : 0u);
@@ -175,20 +186,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* _
       const int kbase = j * kAttBN;
       const bool ragged = kbase + kAttBN > L;
       // all 128 scores of the row in registers: four tcgen05.ld in flight, one wait
-      uint32_t v[4][32];
+      uint32_t v[NC][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_s + lane_addr + c * 32, v[c]);
+      for (int c = 0; c < NC; ++c) tmem_ld_32x32b_x32(tmem_s + lane_addr + c * 32, v[c]);
       tmem_ld_wait();
       if (ragged) {  // only the last block of a sequence whose length is not a multiple of 128
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (kbase + c * 32 + i >= L) v[c][i] = 0xff800000u;  // -inf: exp2 -> 0, never the max
       }
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[c][i]));
       const float m_new = fmaxf(m_run, mx * scale_log2e);   // finite: every block has >= 1 valid key
@@ -196,7 +207,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* _
       // p = exp2(s*scale - m) (masked keys: exp2(-inf) = 0), row sum, bf16 P into the swizzled K-major tile
       float rs = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NC; ++c) {
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -264,23 +275,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int32_t* _
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kAttTmemCols);
+  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+template <int BN>
+static int launch_attention_tc_t(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const int32_t* cu_seqlens, int n_seqs,
+                                 int max_len, int H, int heads, void* ctx, cudaStream_t stream) {
+  using C = AttCfg<BN>;
+  auto kern = attention_tc_kernel<BN>;
+  CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::smem_bytes())));
+  const dim3 grid((max_len + kAttBM - 1) / kAttBM, heads, n_seqs);
+  const float scale_log2e = 1.4426950408889634f / sqrtf(float(kAttDH));
+  kern<<<grid, kAttThreads, C::smem_bytes(), stream>>>(tm_q, tm_kv, cu_seqlens, H, scale_log2e, static_cast<__nv_bfloat16*>(ctx));
+  CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
 }
 
 int launch_attention_tc(const void* qkv, const int32_t* cu_seqlens, int n_seqs, int total_tokens, int max_len, int H,
-                        int heads, void* ctx, cudaStream_t stream) {
+                        int heads, void* ctx, cudaStream_t stream, int block_keys) {
   if (n_seqs <= 0 || max_len <= 0 || total_tokens <= 0) return CRAG_OK;
   if (H / heads != kAttDH) return fail(CRAG_ERR_UNSUPPORTED, "attention_tc: head dim must be 64");
-  CUtensorMap tm;
-  int rc = make_tmap_bf16_2d(&tm, qkv, uint64_t(total_tokens), uint64_t(3) * H, uint64_t(3) * H * 2, 128);
+  CUtensorMap tm_q, tm_kv;
+  int rc = make_tmap_bf16_2d(&tm_q, qkv, uint64_t(total_tokens), uint64_t(3) * H, uint64_t(3) * H * 2, 128);
   if (rc != CRAG_OK) return rc;
-  CRAG_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAttSmemBytes)));
-  const dim3 grid((max_len + kAttBM - 1) / kAttBM, heads, n_seqs);
-  const float scale_log2e = 1.4426950408889634f / sqrtf(float(kAttDH));
-  attention_tc_kernel<<<grid, kAttThreads, kAttSmemBytes, stream>>>(tm, cu_seqlens, H, scale_log2e,
-                                                                    static_cast<__nv_bfloat16*>(ctx));
-  CRAG_CUDA_OK(cudaGetLastError());
-  return CRAG_OK;
+  rc = make_tmap_bf16_2d(&tm_kv, qkv, uint64_t(total_tokens), uint64_t(3) * H, uint64_t(3) * H * 2, block_keys == 128 ? 128 : 64);
+  if (rc != CRAG_OK) return rc;
+  if (block_keys == 128) return launch_attention_tc_t<128>(tm_q, tm_kv, cu_seqlens, n_seqs, max_len, H, heads, ctx, stream);
+  return launch_attention_tc_t<64>(tm_q, tm_kv, cu_seqlens, n_seqs, max_len, H, heads, ctx, stream);
 }
 
 }  // namespace crag

@@ -25,7 +25,8 @@ GEMM_CASES = [  # M, N, K, epi, variant (0 = default dispatch: CTA-pair kernel w
 ATTN_CASES = [  # H, heads, lengths, tc (1 = tcgen05 kernel)
     (128, 4, [5, 64, 65, 1, 130], 0), (1024, 16, [512, 33, 200, 512], 0), (384, 12, [77, 512, 300], 0), (768, 12, [128] * 6, 0),
     (128, 2, [5, 64, 65, 1, 130, 128, 129, 300], 1), (1024, 16, [512, 33, 200, 512], 1), (768, 12, [128] * 6, 1),
-    (1024, 16, [512] * 32, 0), (1024, 16, [512] * 32, 1),
+    (1024, 16, [512] * 32, 0), (1024, 16, [512] * 32, 1), (1024, 16, [512] * 32, 2),
+    (128, 2, [5, 64, 65, 1, 130, 128, 129, 300], 2), (1024, 16, [37, 512, 100, 64, 63, 191, 192, 193], 1),
 ]
 ENC_CASES = [  # name, cfg args, lengths, std
     ("tiny", (128, 2, 4, 256, 1000), [5, 64, 65, 1, 130, 17], 0.02),
@@ -93,7 +94,7 @@ def attn_case(i):
     ctx = torch.zeros(T, H, dtype=torch.bfloat16, device=dev)
     def run():
         if tc:
-            rc = lib.crag_attention_varlen_tc(qkv.data_ptr(), cu.data_ptr(), len(lens), T, max(lens), H, heads, ctx.data_ptr(),
+            rc = lib.crag_attention_varlen_tc(qkv.data_ptr(), cu.data_ptr(), len(lens), T, max(lens), H, heads | ((tc - 1) << 8), ctx.data_ptr(),
                                               torch.cuda.current_stream().cuda_stream)
         else:
             rc = lib.crag_attention_varlen(qkv.data_ptr(), cu.data_ptr(), len(lens), max(lens), H, heads, ctx.data_ptr(),
