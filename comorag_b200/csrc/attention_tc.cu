@@ -197,23 +197,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           for (int i = 0; i < 32; ++i)
             if (kbase + c * 32 + i >= L) v[c][i] = 0xff800000u;  // -inf: exp2 -> 0, never the max
       }
-      float mx = -INFINITY;
+      // block max with 4 independent chains
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < NC; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[c][i]));
-      const float m_new = fmaxf(m_run, mx * scale_log2e);   // finite: every block has >= 1 valid key
-      const float alpha = att_exp2(m_run - m_new);
-      // p = exp2(s*scale - m) (masked keys: exp2(-inf) = 0), row sum, bf16 P into the swizzled K-major tile
-      float rs = 0.f;
+        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale_log2e;  // finite: >= 1 valid key
+      // Lazy rescaling: the reference point m_run only moves when the true max has grown by more than 2^8; until
+      // then p = exp2(s - m_run) may exceed 1 (<= 256), which fp32 sums and bf16 P hold without loss, and O / l is
+      // unchanged mathematically.  Saves the TMEM round trip of O for almost every block.
+      float alpha = 1.0f;
+      if (mx > m_run + 8.0f) {
+        alpha = att_exp2(m_run - mx);   // first block: exp2(-inf) = 0
+        m_run = mx;
+      }
+      const bool rescale = j > 0 && __any_sync(0xffffffffu, alpha != 1.0f);
+      // p = exp2(s*scale - m) (masked keys: exp2(-inf) = 0), row sums in 4 chains, bf16 P into the swizzled tile
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = att_exp2(fmaf(__uint_as_float(v[c][2 * i]), scale_log2e, -m_new));
-          const float p1 = att_exp2(fmaf(__uint_as_float(v[c][2 * i + 1]), scale_log2e, -m_new));
-          rs += p0 + p1;
+          const float p0 = att_exp2(fmaf(__uint_as_float(v[c][2 * i]), scale_log2e, -m_run));
+          const float p1 = att_exp2(fmaf(__uint_as_float(v[c][2 * i + 1]), scale_log2e, -m_run));
+          rs4[i & 3] += p0 + p1;
           __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
           packed[i] = *reinterpret_cast<uint32_t*>(&b);
         }
@@ -226,18 +235,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
         }
       }
-      l_run = l_run * alpha + rs;
-      m_run = m_new;
+      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       // rescale the running O (P_{j-1} V_{j-1} has retired: S_j's commit covers it)
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+      if (rescale) {
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_o + lane_addr + c * 32, v);
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tmem_o + lane_addr + c * 32, o);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st_32x32b_x32(tmem_o + lane_addr + c * 32, v);
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32b_x32(tmem_o + lane_addr + c * 32, o);
         }
         tmem_st_wait();
       }
