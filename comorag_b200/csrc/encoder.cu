@@ -119,12 +119,10 @@ extern "C" int crag_attention_varlen(const void* qkv, const int32_t* cu_seqlens,
 extern "C" int crag_attention_varlen_tc(const void* qkv, const int32_t* cu_seqlens, int n_seqs, int total_tokens,
                                         int max_seqlen, int hidden_size, int heads, void* ctx, crag_stream_t stream) {
   if (!qkv || !cu_seqlens || !ctx) return fail(CRAG_ERR_INVALID, "attention: null pointer");
-  // bits 8+ of `heads` select the key-block size for A/B testing (0 = default 64, 1 = 128)
-  const int variant = heads >> 8;
   heads &= 0xFF;
   if (heads < 1 || hidden_size % heads || hidden_size / heads != 64) return fail(CRAG_ERR_UNSUPPORTED, "attention_tc: head dim must be 64");
   return launch_attention_tc(qkv, cu_seqlens, n_seqs, total_tokens, max_seqlen, hidden_size, heads, ctx,
-                             static_cast<cudaStream_t>(stream), variant == 1 ? 128 : 64);
+                             static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int crag_layernorm(const void* in, int rows, int hidden_size, const float* gamma, const float* beta,

@@ -14,7 +14,7 @@ int launch_layernorm(const void* in, int T, int H, const float* gamma, const flo
 int launch_attention(const void* qkv, const int32_t* cu_seqlens, int n_seqs, int max_len, int H, int heads, void* ctx,
                      cudaStream_t stream);
 int launch_attention_tc(const void* qkv, const int32_t* cu_seqlens, int n_seqs, int total_tokens, int max_len, int H,
-                        int heads, void* ctx, cudaStream_t stream, int block_keys = 64);
+                        int heads, void* ctx, cudaStream_t stream);
 int launch_pool_normalize(const void* hidden, const int32_t* cu_seqlens, int n_seqs, int H, int normalize,
                           float* out_f32, void* out_bf16, int64_t out_bf16_stride, cudaStream_t stream);
 
