@@ -88,8 +88,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* bar_s_free = bar_s_full + 2;   // [2] S_j pulled into registers (4 warps)
   uint64_t* bar_p_full = bar_s_free + 2;   // [2] P_j written (4 warps)
   uint64_t* bar_p_free = bar_p_full + 2;   // [2] P_j V_j retired: buffer reusable
-  uint64_t* bar_pv = bar_p_free + 2;       // phase j: P_j V_j retired (O stable)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_pv + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_p_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -106,7 +105,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_init(&bar_p_full[s], 4);
       mbar_init(&bar_p_free[s], 1);
     }
-    mbar_init(bar_pv, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -170,7 +168,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                    (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&bar_v_empty[st]);
         umma_commit(&bar_p_free[st]);
-        umma_commit(bar_pv);
       }
     }
   } else {
@@ -214,7 +211,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         m_run = mx;
       }
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-        mbar_wait(bar_pv, (j - 1) & 1);   // P_{j-1} V_{j-1} retired; P_j V_j cannot start before this warp's p_full
+        // P_{j-1} V_{j-1} retired (P_j V_j cannot start before this warp's p_full).  p_free[(j-1)&1] is at most one
+        // phase behind here (block j-1 already waited for P_{j-3} V_{j-3} on it), so the parity test is unambiguous.
+        mbar_wait(&bar_p_free[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
@@ -254,7 +253,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (lane == 0) mbar_arrive(&bar_p_full[st]);
     }
     // epilogue: O / l -> bf16 -> ctx[start + q0 + r, head*64 .. +64)
-    mbar_wait(bar_pv, (n_blk - 1) & 1);
+    mbar_wait(&bar_p_free[(n_blk - 1) & 1], ((n_blk - 1) >> 1) & 1);   // last P V retired (they retire in order)
     tc_fence_after();
     const float inv = 1.f / l_run;
     const int row = q0 + r;
