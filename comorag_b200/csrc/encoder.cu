@@ -82,7 +82,10 @@ extern "C" int crag_encoder_forward(const crag_encoder* model, const int32_t* to
     const crag_encoder_layer& w = model->layers[l];
     rc = gemm_bf16(b.x, H, w.w_qkv, H, w.b_qkv, nullptr, 0, b.qkv, 3 * H, T, 3 * H, H, GEMM_EPI_BIAS, stream);
     if (rc != CRAG_OK) return rc;
-    rc = launch_attention(b.qkv, cu_seqlens, n_seqs, max_seqlen, H, model->heads, b.ctx, stream);
+    // head dim 64 (bge-base / bge-large): tcgen05 kernel; head dim 32 (bge-small): mma.sync kernel
+    rc = (H / model->heads == 64)
+             ? launch_attention_tc(b.qkv, cu_seqlens, n_seqs, T, max_seqlen, H, model->heads, b.ctx, stream)
+             : launch_attention(b.qkv, cu_seqlens, n_seqs, max_seqlen, H, model->heads, b.ctx, stream);
     if (rc != CRAG_OK) return rc;
     rc = gemm_bf16(b.ctx, H, w.w_o, H, w.b_o, b.x, H, b.tmp, H, T, H, H, GEMM_EPI_BIAS_RESIDUAL, stream);
     if (rc != CRAG_OK) return rc;

@@ -52,9 +52,11 @@ def test_gemm_epilogues(dev, M, N, K, epi):
     assert bool((err <= 0.01 * ref.abs() + 0.02).all()), float(err.max())   # bf16 output rounding
 
 
-@pytest.mark.parametrize("H,heads,lens", [(128, 4, [5, 64, 65, 1, 130]), (1024, 16, [512, 33, 200]), (384, 12, [77, 512]),
-                                          (768, 12, [128] * 3)])
-def test_varlen_attention(dev, H, heads, lens):
+@pytest.mark.parametrize("H,heads,lens,tc", [(128, 4, [5, 64, 65, 1, 130], 0), (1024, 16, [512, 33, 200], 0), (384, 12, [77, 512], 0),
+                                             (768, 12, [128] * 3, 0), (128, 2, [5, 64, 65, 1, 130, 128, 129, 300, 512], 1),
+                                             (1024, 16, [512, 33, 200, 511], 1), (768, 12, [128, 63, 64], 1)])
+def test_varlen_attention(dev, H, heads, lens, tc):
+    """tc=0: mma.sync kernel (any head dim in {32, 64}); tc=1: tcgen05 kernel (head dim 64)."""
     from comorag_b200 import _native
     lib = _native.load()
     dh, T = H // heads, sum(lens)
@@ -62,8 +64,11 @@ def test_varlen_attention(dev, H, heads, lens):
     qkv = torch.randn(T, 3 * H, generator=g, device=dev).bfloat16()
     cu = torch.tensor([0] + np.cumsum(lens).tolist(), dtype=torch.int32, device=dev)
     ctx = torch.full((T, H), float("nan"), dtype=torch.bfloat16, device=dev)
-    rc = lib.crag_attention_varlen(qkv.data_ptr(), cu.data_ptr(), len(lens), max(lens), H, heads, ctx.data_ptr(),
-                                   torch.cuda.current_stream().cuda_stream)
+    st = torch.cuda.current_stream().cuda_stream
+    if tc:
+        rc = lib.crag_attention_varlen_tc(qkv.data_ptr(), cu.data_ptr(), len(lens), T, max(lens), H, heads, ctx.data_ptr(), st)
+    else:
+        rc = lib.crag_attention_varlen(qkv.data_ptr(), cu.data_ptr(), len(lens), max(lens), H, heads, ctx.data_ptr(), st)
     _native.check(rc, "crag_attention_varlen")
     ref, s = torch.zeros(T, H, device=dev), 0
     for L in lens:
