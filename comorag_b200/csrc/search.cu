@@ -202,16 +202,30 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       }
       while (true) {
         bool want_flush = false;
+        // Warp-aggregated push: one ballot per query (warp-uniform branch, no divergence in the common
+        // no-candidate case) and ONE shared-memory atomic per (warp, query) however many lanes have a candidate.
 #pragma unroll
         for (int q = 0; q < kNQ; ++q) {
-          if (((pending >> q) & 1u) && make_key(__uint_as_float(r[q]), uint32_t(row)) >= bnd_key[q]) pending &= ~(1u << q);
-          if ((pending >> q) & 1u) {
-            const int slot = atomicAdd(&cnt[q], 1);
-            if (slot < CAP) {
-              keys[q * L::kKeysPerQuery + KLIST + slot] = make_key(__uint_as_float(r[q]), uint32_t(row));
-              pending &= ~(1u << q);
+          const bool mine = (pending >> q) & 1u;
+          if (__ballot_sync(0xffffffffu, mine) != 0u) {
+            const uint64_t key = make_key(__uint_as_float(r[q]), uint32_t(row));
+            const bool ok = mine && key < bnd_key[q];          // "search after" bound (all ones = no bound)
+            if (mine && !ok) pending &= ~(1u << q);
+            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+            if (m != 0u) {
+              const int leader = __ffs(m) - 1;
+              int base = 0;
+              if (lane == leader) base = atomicAdd(&cnt[q], __popc(m));
+              base = __shfl_sync(0xffffffffu, base, leader);
+              if (ok) {
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < CAP) {
+                  keys[q * L::kKeysPerQuery + KLIST + slot] = key;
+                  pending &= ~(1u << q);
+                }
+                if (slot >= CAP - 1) want_flush = true;
+              }
             }
-            if (slot >= CAP - 1) want_flush = true;
           }
         }
         if (!named_bar_or(1, kEpiThreads, want_flush || pending != 0)) break;
@@ -283,6 +297,34 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
 // selector.  PAIRS=false: raw keys (local row ids) from search_topk_kernel's
 // CTAs, ids are widened and offset on output.  PAIRS=true: (score, int64 id)
 // pairs from several shards; ties resolve by candidate position.
+// One warp streams `total` candidate keys (fetch(i), 0 = absent) through a KLIST+CAP selector (CAP >= 32).
+template <int KLIST, int CAP, class Fetch>
+__device__ __forceinline__ void select_stream(uint64_t* keys, uint64_t* thr_slot, int lane, int k, int total,
+                                              uint64_t bound, Fetch fetch) {
+  static_assert(CAP >= 32, "a batch of 32 candidates must fit the buffer");
+  for (int i = lane; i < KLIST + CAP; i += 32) keys[i] = 0ull;
+  if (lane == 0) *thr_slot = 0ull;
+  __syncwarp();
+  int c = 0;
+  for (int base = 0; base < total; base += 32) {
+    const int idx = base + lane;
+    const uint64_t key = idx < total ? fetch(idx) : 0ull;
+    const uint64_t thr = *thr_slot > bound ? *thr_slot : bound;
+    const bool take = key != 0 && key >= thr;
+    const uint32_t m = __ballot_sync(0xffffffffu, take);
+    if (take) keys[KLIST + c + __popc(m & ((1u << lane) - 1u))] = key;
+    c += __popc(m);
+    __syncwarp();
+    if (c + 32 > CAP) {
+      flush_query<KLIST, CAP>(keys, c, k, thr_slot, lane);
+      c = 0;
+    }
+  }
+  if (c > 0) flush_query<KLIST, CAP>(keys, c, k, thr_slot, lane);
+  __syncwarp();
+}
+
+// One CTA (4 warps) per query: warp w merges parts w, w+4, ... into its own list, warp 0 merges the four lists.
 template <int KLIST, int CAP, bool PAIRS>
 __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restrict__ part_keys,
                                                          const float* __restrict__ in_scores,
@@ -295,21 +337,14 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
                                                          float* __restrict__ out_minmax,
                                                          uint64_t* __restrict__ last_keys) {
   constexpr int KPQ = KLIST + CAP;
-  __shared__ uint64_t s_keys[4][KPQ];
-  __shared__ uint64_t s_thr[4];
+  __shared__ uint64_t s_keys[5][KPQ];
+  __shared__ uint64_t s_thr[5];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * 4 + w;
-  if (q >= nq) return;
-  uint64_t* keys = s_keys[w];
-  for (int i = lane; i < KPQ; i += 32) keys[i] = 0ull;
-  if (lane == 0) s_thr[w] = 0ull;
-  __syncwarp();
+  const int q = blockIdx.x;
 
-  int c = 0;
-  const int total = parts * k;
   // Admission bound before any sorting: every part's list is sorted, so its k-th entry is a lower bound of the
-  // global k-th best (that part alone already holds k candidates at least that good).  Taking the max over parts
-  // rejects almost all of the parts*k candidates up front and leaves one flush for the common case.
+  // global k-th best (that part alone already holds k candidates at least that good); the max over parts rejects
+  // almost all of the parts*k candidates up front.
   uint64_t bound = 0;
   if (!PAIRS) {
     for (int p = lane; p < parts; p += 32) {
@@ -322,33 +357,22 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
       bound = other > bound ? other : bound;
     }
   }
-  for (int base = 0; base < total; base += 32) {
-    const int idx = base + lane;
-    uint64_t key = 0;
-    if (idx < total) {
-      const int p = idx / k, j = idx - p * k;
-      if (PAIRS) {
-        const size_t at = size_t(q) * k + j;
-        const int64_t id = *reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(in_ids + at) + p * ids_stride);
-        const float sc = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(in_scores + at) + p * scores_stride);
-        if (id >= 0) key = make_key(sc, uint32_t(idx));
-      } else {
-        key = part_keys[(size_t(p) * q_stride + q) * k + j];
-      }
+  const int my_parts = parts > w ? (parts - w + 3) / 4 : 0;
+  select_stream<KLIST, CAP>(s_keys[w], &s_thr[w], lane, k, my_parts * k, bound, [&](int idx) -> uint64_t {
+    const int pl = idx / k, j = idx - pl * k, p = w + 4 * pl;
+    if (PAIRS) {
+      const size_t at = size_t(q) * k + j;
+      const int64_t id = *reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(in_ids + at) + p * ids_stride);
+      const float sc = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(in_scores + at) + p * scores_stride);
+      return id >= 0 ? make_key(sc, uint32_t(p * k + j)) : 0ull;
     }
-    const uint64_t thr = s_thr[w] > bound ? s_thr[w] : bound;
-    const bool take = key != 0 && key >= thr;
-    const uint32_t m = __ballot_sync(0xffffffffu, take);
-    if (take) keys[KLIST + c + __popc(m & ((1u << lane) - 1u))] = key;
-    c += __popc(m);
-    __syncwarp();
-    if (c + 32 > CAP) {
-      flush_query<KLIST, CAP>(keys, c, k, &s_thr[w], lane);
-      c = 0;
-    }
-  }
-  if (c > 0) flush_query<KLIST, CAP>(keys, c, k, &s_thr[w], lane);
-  __syncwarp();
+    return part_keys[(size_t(p) * q_stride + q) * k + j];
+  });
+  __syncthreads();
+  if (w != 0) return;
+  uint64_t* keys = s_keys[4];
+  select_stream<KLIST, CAP>(keys, &s_thr[4], lane, k, 4 * k, 0ull,
+                            [&](int idx) -> uint64_t { return s_keys[idx / k][idx % k]; });
   for (int j = lane; j < k; j += 32) {
     const uint64_t key = keys[j];
     float s = -INFINITY;
@@ -465,6 +489,10 @@ int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_st
   rc = make_tmap_bf16_2d(&tm_q, queries, uint64_t(nq), uint64_t(dim), uint64_t(dim) * 2, kNQ);
   if (rc != CRAG_OK) return rc;
   const int num_kb = dim / kBlockK;
+  // small candidate buffers keep the admission thresholds fresh (a threshold only moves when a buffer is flushed)
+  // and make a flush a 32- or 64-key sort; the smem they free goes to TMA stages
+  if (k <= 16) return launch_search<16, 16, 9>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, part_keys, part_minmax, stream);
+  if (k <= 32) return launch_search<32, 32, 8>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, part_keys, part_minmax, stream);
   if (k <= 64) return launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, part_keys, part_minmax, stream);
   return launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, part_keys, part_minmax, stream);
 }
@@ -475,8 +503,10 @@ int finalize_pass(const void* workspace, int64_t n_rows, int nq, int k, int64_t 
   const int grid = scan_grid(n_rows, plan);
   const uint64_t* part_keys = static_cast<const uint64_t*>(workspace);
   const float* part_minmax = reinterpret_cast<const float*>(static_cast<const uint8_t*>(workspace) + plan.keys_bytes);
-  const int mgrid = (nq + 3) / 4;
-  if (k <= 64)
+  const int mgrid = nq;  // one CTA per query
+  if (k <= 32)
+    merge_topk_kernel<32, 32, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, 0, 0, 0, out_ids, out_scores, out_minmax, last_keys);
+  else if (k <= 64)
     merge_topk_kernel<64, 64, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, 0, 0, 0, out_ids, out_scores, out_minmax, last_keys);
   else
     merge_topk_kernel<128, 128, false><<<mgrid, 128, 0, stream>>>(part_keys, nullptr, nullptr, part_minmax, grid, kNQ, nq, k, row_offset, 0, 0, 0, out_ids, out_scores, out_minmax, last_keys);
@@ -544,9 +574,11 @@ int merge_pairs(const float* scores, const int64_t* ids, const float* minmax, in
                 cudaStream_t stream) {
   if (parts < 0 || nq < 1 || k < 1 || k > 128 || int64_t(parts) * k > (1 << 20)) return fail(CRAG_ERR_INVALID, "crag_merge_topk: bad sizes (parts=%d nq=%d k=%d)", parts, nq, k);
   if (!out_ids || !out_scores || (parts > 0 && (!scores || !ids))) return fail(CRAG_ERR_INVALID, "crag_merge_topk: null pointer");
-  const int mgrid = (nq + 3) / 4;
+  const int mgrid = nq;  // one CTA per query
   const float* mm = out_minmax ? minmax : nullptr;
-  if (k <= 64)
+  if (k <= 32)
+    merge_topk_kernel<32, 32, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, mm, parts, nq, nq, k, 0, ids_stride, scores_stride, mm_stride, out_ids, out_scores, out_minmax, nullptr);
+  else if (k <= 64)
     merge_topk_kernel<64, 64, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, mm, parts, nq, nq, k, 0, ids_stride, scores_stride, mm_stride, out_ids, out_scores, out_minmax, nullptr);
   else
     merge_topk_kernel<128, 128, true><<<mgrid, 128, 0, stream>>>(nullptr, scores, ids, mm, parts, nq, nq, k, 0, ids_stride, scores_stride, mm_stride, out_ids, out_scores, out_minmax, nullptr);

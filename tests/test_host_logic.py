@@ -60,3 +60,30 @@ def test_pack_unpack_roundtrip_and_merge_rule():
     assert torch.equal(os_, flat_s.sort(dim=1, descending=True).values[:, :k])
     assert torch.equal(om[:, 0], mm[..., 0].min(0).values) and torch.equal(om[:, 1], mm[..., 1].max(0).values)
     assert (oi >= 0).all()
+
+
+def test_rerank_surface_keeps_reference_contract():
+    """DSPyFilter(narrtiverag)(query, candidate_items, candidate_indices, len_after_rerank) -> (indices, items, dict)
+    (rerank.py:97-123); ranking rule: dense similarity of "s p o" to the query, ties by candidate position."""
+    import types
+    from comorag_b200.rerank import DSPyFilter
+
+    vocab = {"cinderella": 0, "prince": 1, "slipper": 2, "pumpkin": 3}
+
+    class Model:
+        def batch_encode(self, texts, **kw):
+            out = np.zeros((len(texts), 4), np.float32)
+            for i, t in enumerate(texts):
+                for w in t.lower().split():
+                    if w in vocab:
+                        out[i, vocab[w]] += 1
+            return out
+
+    rag = types.SimpleNamespace(global_config=types.SimpleNamespace(), embedding_model=Model())
+    f = DSPyFilter(rag)
+    items = [("pumpkin", "became", "coach"), ("prince", "found", "slipper"), ("cinderella", "lost", "slipper")]
+    idx, kept, meta = f("who found the slipper prince", items, [10, 11, 12], len_after_rerank=2)
+    assert idx == [11, 12] and kept == [items[1], items[2]] and len(meta["confidence"]) == 2
+    assert f.rerank("x", [], [], 3) == ([], [], {"confidence": None})
+    idx_all, _, _ = f("slipper", items, [0, 1, 2])          # len_after_rerank=None keeps everything
+    assert idx_all == [1, 2, 0]                              # tie between items 1 and 2 -> candidate order

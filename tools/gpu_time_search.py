@@ -15,7 +15,7 @@ from util_search import make_unit_rows
 def main():
     lib = _native.load()
     dev = torch.device("cuda:0")
-    nq, k, dim = 32, int(os.environ.get("K", "10")), 1024
+    nq, k, dim = int(os.environ.get("NQ", "32")), int(os.environ.get("K", "10")), 1024
     q = make_unit_rows(nq, dim, 5, device=dev)
     big = make_unit_rows(10_000_000, dim, 6, device=dev)
     st = torch.cuda.current_stream()
@@ -23,7 +23,8 @@ def main():
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     ids = torch.empty(nq, k, dtype=torch.int64, device=dev); sc = torch.empty(nq, k, device=dev); mm = torch.empty(nq, 2, device=dev)
     out = []
-    for rows in [78_125, 156_250, 312_500, 625_000, 1_250_000, 2_500_000, 5_000_000, 10_000_000]:
+    sizes = [int(x) for x in os.environ["ROWS"].split(",")] if "ROWS" in os.environ else [78_125, 156_250, 312_500, 625_000, 1_250_000, 2_500_000, 5_000_000, 10_000_000]
+    for rows in sizes:
         corpus = big[:rows]
 
         def scan():
@@ -46,7 +47,7 @@ def main():
         out.append({"rows": rows, "scan_us": round(t_scan, 1), "scan+finalize_us": round(t_both, 1), "ideal_us@7.15TB/s": round(ideal, 1),
                     "overhead_us": round(t_both - ideal, 1)})
         print(json.dumps(out[-1]), flush=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"time_search_k{k}.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"time_search_k{k}_nq{nq}.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
