@@ -46,13 +46,82 @@ struct SearchLayout {
            + kNQ * 4               // thr_f
            + kNQ * 4               // cnt
            + kNQ * 8 + kNQ * 4     // continuation bound (key, score)
-           + 4 * kNQ * 2 * 4       // min/max cross-warp reduction
+           + kNQ * 4 * 5           // done, running min, running max (+ slack)
            + 16;                   // tmem base
   }
   __host__ static size_t smem_bytes(int num_kb) {
     return 1024 + size_t(STAGES) * kStageBytes + size_t(num_kb) * kQBlockBytes + keys_bytes() + misc_bytes();
   }
 };
+
+// Shared selector state of one CTA (all pointers into shared memory).
+struct SelectorState {
+  uint64_t* keys;      // [kNQ][KLIST + CAP]
+  uint64_t* thr_key;   // [kNQ] current k-th best key (0 while fewer than k are held)
+  float* thr_f;        // [kNQ] its score (-inf while fewer than k are held)
+  int* cnt;            // [kNQ] candidate slots reserved since the last flush
+  int* done;           // [kNQ] candidate slots written since the last flush
+  const uint64_t* bnd_key;  // [kNQ] "search after" bound
+};
+
+// Offer this warp's candidates for query q (lane holds `key`, `mine` says whether it is a candidate).  Called by all
+// 32 lanes.  Slots are reserved with ONE shared-memory atomic per call; the warp whose reservation fills the buffer
+// flushes it (after every reserved slot has been written) and reopens it; warps that find it full wait and retry.
+// No CTA-wide barrier: a warp never blocks between reserving and writing its slots, so the waits cannot cycle.
+template <int KLIST, int CAP>
+__device__ __noinline__ void push_candidates(const SelectorState sel, int q, uint64_t key, bool mine, int k, int lane) {
+  uint64_t* qkeys = sel.keys + q * (KLIST + CAP);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  while (true) {
+    // exact admission against the CURRENT threshold and the "search after" bound
+    const bool ok = mine && key < sel.bnd_key[q] && key > *reinterpret_cast<volatile uint64_t*>(&sel.thr_key[q]);
+    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if (m == 0u) return;
+    const int n = __popc(m), leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&sel.cnt[q], n);
+    base = __shfl_sync(0xffffffffu, base, leader);
+    const int slot = base + __popc(m & lt_mask);
+    const bool wrote = ok && slot < CAP;
+    if (wrote) qkeys[KLIST + slot] = key;
+    const int nw = __popc(__ballot_sync(0xffffffffu, wrote));
+    __syncwarp();
+    if (nw && lane == leader) {
+      __threadfence_block();
+      atomicAdd(&sel.done[q], nw);  // publish: nw more slots hold valid keys
+    }
+    mine = ok && !wrote;            // overflowed lanes retry after the flush
+    if (base + n < CAP) return;     // buffer not full
+    if (base < CAP) {
+      // this reservation filled the buffer: flush once every reserved slot has been written
+      while (*reinterpret_cast<volatile int*>(&sel.done[q]) < CAP) __nanosleep(20);
+      __threadfence_block();
+      flush_query<KLIST, CAP>(qkeys, CAP, k, &sel.thr_key[q], lane);
+      if (lane == 0) {
+        const uint64_t t = sel.thr_key[q];
+        sel.thr_f[q] = t ? key_score(t) : -INFINITY;
+        sel.done[q] = 0;
+        __threadfence_block();
+        *reinterpret_cast<volatile int*>(&sel.cnt[q]) = 0;  // reopens the buffer
+      }
+      __syncwarp();
+    } else {
+      // already full when this warp arrived: wait for the flushing warp to reopen it
+      while (*reinterpret_cast<volatile int*>(&sel.cnt[q]) >= CAP) __nanosleep(40);
+      __threadfence_block();
+    }
+  }
+}
+
+// float min/max on shared memory through the integer atomics (sign-split trick; works for mixed signs and +-inf)
+__device__ __forceinline__ void smem_atomic_min_f32(float* addr, float v) {
+  if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void smem_atomic_max_f32(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
 
 template <int KLIST, int CAP, int STAGES>
 __global__ void __launch_bounds__(kSearchThreads, 1)
@@ -74,8 +143,10 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   uint64_t* thr_key = bar_q + 1;              // [kNQ]
   float* thr_f = reinterpret_cast<float*>(thr_key + kNQ);  // [kNQ]
   int* cnt = reinterpret_cast<int*>(thr_f + kNQ);          // [kNQ]
-  float* red = reinterpret_cast<float*>(cnt + kNQ);        // [4][kNQ][2]
-  uint64_t* bnd_key = reinterpret_cast<uint64_t*>(red + 4 * kNQ * 2);  // [kNQ] admit only keys < bnd_key
+  int* done = cnt + kNQ;                                   // [kNQ] candidate slots already written
+  float* mn_f = reinterpret_cast<float*>(done + kNQ);      // [kNQ] running min over the CTA's rows
+  float* mx_f = mn_f + kNQ;                                // [kNQ] running max
+  uint64_t* bnd_key = reinterpret_cast<uint64_t*>(mx_f + kNQ + 2 * kNQ);  // [kNQ] admit only keys < bnd_key
   float* bnd_f = reinterpret_cast<float*>(bnd_key + kNQ);              // [kNQ] score part of the bound
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bnd_f + kNQ);
 
@@ -108,6 +179,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
     thr_key[threadIdx.x] = 0ull;
     thr_f[threadIdx.x] = -INFINITY;
     cnt[threadIdx.x] = 0;
+    done[threadIdx.x] = 0;
+    mn_f[threadIdx.x] = INFINITY;
+    mx_f[threadIdx.x] = -INFINITY;
     // "search after": rank continuation for k > 128 -- only candidates strictly below the previous pass's last key
     const uint64_t b = (after_keys != nullptr && int(threadIdx.x) < nq) ? after_keys[threadIdx.x] : ~0ull;
     bnd_key[threadIdx.x] = b;
@@ -169,11 +243,13 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
     }
   } else {
     // ================================================================== select
+    // Each select warp runs at its own pace (no CTA-wide barrier per tile).  Per tile a thread only COMPARES its
+    // 32 scores against the query's admission threshold and running (min, max), all read from shared memory;
+    // the rare hits take the slow paths below.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int ew = warp - 2;    // select-warp index 0..3 (query ownership for flushes)
-    float mn[kNQ], mx[kNQ];
-#pragma unroll
-    for (int q = 0; q < kNQ; ++q) { mn[q] = INFINITY; mx[q] = -INFINITY; }
+    const int ew = warp - 2;    // select-warp index 0..3 (query ownership for the final drain)
+    const uint32_t q_mask = nq < kNQ ? (1u << nq) - 1u : 0xffffffffu;
+    const SelectorState sel{keys, thr_key, thr_f, cnt, done, bnd_key};
 
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -189,64 +265,38 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
 
       const int row = tile * kTileRows + quad * 32 + lane;
-      uint32_t pending = 0;
+      uint32_t pend_top = 0, pend_mm = 0;
       if (row < n_rows) {
 #pragma unroll
         for (int q = 0; q < kNQ; ++q) {
           const float s = __uint_as_float(r[q]);
-          mn[q] = fminf(mn[q], s);
-          mx[q] = fmaxf(mx[q], s);
-          if (s >= thr_f[q] && s <= bnd_f[q]) pending |= 1u << q;
+          if (s >= thr_f[q] && s <= bnd_f[q]) pend_top |= 1u << q;
+          if (s < mn_f[q] || s > mx_f[q]) pend_mm |= 1u << q;
         }
-        if (nq < kNQ) pending &= (1u << nq) - 1u;
+        pend_top &= q_mask;
+        pend_mm &= q_mask;
       }
-      while (true) {
-        bool want_flush = false;
-        // Warp-aggregated push: one ballot per query (warp-uniform branch, no divergence in the common
-        // no-candidate case) and ONE shared-memory atomic per (warp, query) however many lanes have a candidate.
+      // running (min, max): a new extreme is a 1/i event for the i-th row -> a handful of smem atomics per query
+      const uint32_t wm_mm = __reduce_or_sync(0xffffffffu, pend_mm);
+      if (wm_mm) {
 #pragma unroll
         for (int q = 0; q < kNQ; ++q) {
-          const bool mine = (pending >> q) & 1u;
-          if (__ballot_sync(0xffffffffu, mine) != 0u) {
-            const uint64_t key = make_key(__uint_as_float(r[q]), uint32_t(row));
-            const bool ok = mine && key < bnd_key[q];          // "search after" bound (all ones = no bound)
-            if (mine && !ok) pending &= ~(1u << q);
-            const uint32_t m = __ballot_sync(0xffffffffu, ok);
-            if (m != 0u) {
-              const int leader = __ffs(m) - 1;
-              int base = 0;
-              if (lane == leader) base = atomicAdd(&cnt[q], __popc(m));
-              base = __shfl_sync(0xffffffffu, base, leader);
-              if (ok) {
-                const int slot = base + __popc(m & ((1u << lane) - 1u));
-                if (slot < CAP) {
-                  keys[q * L::kKeysPerQuery + KLIST + slot] = key;
-                  pending &= ~(1u << q);
-                }
-                if (slot >= CAP - 1) want_flush = true;
-              }
+          if ((wm_mm >> q) & 1u) {
+            if ((pend_mm >> q) & 1u) {
+              const float s = __uint_as_float(r[q]);
+              smem_atomic_min_f32(&mn_f[q], s);
+              smem_atomic_max_f32(&mx_f[q], s);
             }
           }
         }
-        if (!named_bar_or(1, kEpiThreads, want_flush || pending != 0)) break;
-        for (int q = ew; q < kNQ; q += 4) {
-          const int c = cnt[q];
-          if (c >= CAP) {
-            flush_query<KLIST, CAP>(keys + q * L::kKeysPerQuery, CAP, k, &thr_key[q], lane);
-            if (lane == 0) {
-              const uint64_t t = thr_key[q];
-              thr_f[q] = t ? key_score(t) : -INFINITY;
-              cnt[q] = 0;
-            }
-          }
-        }
-        named_bar_sync(1, kEpiThreads);
-        if (pending) {
+      }
+      // top-k candidates
+      const uint32_t wm = __reduce_or_sync(0xffffffffu, pend_top);
+      if (wm) {
 #pragma unroll
-          for (int q = 0; q < kNQ; ++q) {
-            if (((pending >> q) & 1u) && make_key(__uint_as_float(r[q]), uint32_t(row)) < thr_key[q])
-              pending &= ~(1u << q);
-          }
+        for (int q = 0; q < kNQ; ++q) {
+          if ((wm >> q) & 1u)  // warp-uniform
+            push_candidates<KLIST, CAP>(sel, q, make_key(__uint_as_float(r[q]), uint32_t(row)), (pend_top >> q) & 1u, k, lane);
         }
       }
     }
@@ -260,29 +310,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       uint64_t* dst = part_keys + (size_t(blockIdx.x) * kNQ + q) * k;
       for (int j = lane; j < k; j += 32) dst[j] = keys[q * L::kKeysPerQuery + j];
     }
-#pragma unroll
-    for (int q = 0; q < kNQ; ++q) {
-      float a = mn[q], b = mx[q];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
-        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
-      }
-      if (lane == q) {
-        red[(ew * kNQ + q) * 2 + 0] = a;
-        red[(ew * kNQ + q) * 2 + 1] = b;
-      }
-    }
-    named_bar_sync(1, kEpiThreads);
     if (ew == 0) {
-      float a = red[lane * 2], b = red[lane * 2 + 1];
-#pragma unroll
-      for (int w = 1; w < 4; ++w) {
-        a = fminf(a, red[(w * kNQ + lane) * 2]);
-        b = fmaxf(b, red[(w * kNQ + lane) * 2 + 1]);
-      }
-      part_minmax[(size_t(blockIdx.x) * kNQ + lane) * 2 + 0] = a;
-      part_minmax[(size_t(blockIdx.x) * kNQ + lane) * 2 + 1] = b;
+      part_minmax[(size_t(blockIdx.x) * kNQ + lane) * 2 + 0] = mn_f[lane];
+      part_minmax[(size_t(blockIdx.x) * kNQ + lane) * 2 + 1] = mx_f[lane];
     }
   }
 
