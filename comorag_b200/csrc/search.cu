@@ -60,56 +60,47 @@ struct SelectorState {
   uint64_t* thr_key;   // [kNQ] current k-th best key (0 while fewer than k are held)
   float* thr_f;        // [kNQ] its score (-inf while fewer than k are held)
   int* cnt;            // [kNQ] candidate slots reserved since the last flush
-  int* done;           // [kNQ] candidate slots written since the last flush
   const uint64_t* bnd_key;  // [kNQ] "search after" bound
 };
 
-// Offer this warp's candidates for query q (lane holds `key`, `mine` says whether it is a candidate).  Called by all
-// 32 lanes.  Slots are reserved with ONE shared-memory atomic per call; the warp whose reservation fills the buffer
-// flushes it (after every reserved slot has been written) and reopens it; warps that find it full wait and retry.
-// No CTA-wide barrier: a warp never blocks between reserving and writing its slots, so the waits cannot cycle.
+// Slow path of the selector, entered by a whole warp for one query q when some lane's reservation hit the end of
+// the candidate buffer: slot == CAP-1 means "this lane's candidate filled the buffer" (exactly one lane in the CTA
+// per round), slot >= CAP means "arrived while it was full".  The filling warp waits until every reserved slot holds
+// a key (valid keys are non-zero, the region is zeroed after each flush), sorts, publishes the new threshold and
+// reopens the buffer; overflowed lanes then re-offer their candidate against the fresh threshold.
+// No CTA-wide barrier: a warp never blocks between reserving a slot and writing it, so the waits cannot cycle.
 template <int KLIST, int CAP>
-__device__ __noinline__ void push_candidates(const SelectorState sel, int q, uint64_t key, bool mine, int k, int lane) {
+__device__ __noinline__ void resolve_full(const SelectorState sel, int q, uint64_t key, int slot, int k, int lane) {
   uint64_t* qkeys = sel.keys + q * (KLIST + CAP);
-  const uint32_t lt_mask = (1u << lane) - 1u;
   while (true) {
-    // exact admission against the CURRENT threshold and the "search after" bound
-    const bool ok = mine && key < sel.bnd_key[q] && key > *reinterpret_cast<volatile uint64_t*>(&sel.thr_key[q]);
-    const uint32_t m = __ballot_sync(0xffffffffu, ok);
-    if (m == 0u) return;
-    const int n = __popc(m), leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&sel.cnt[q], n);
-    base = __shfl_sync(0xffffffffu, base, leader);
-    const int slot = base + __popc(m & lt_mask);
-    const bool wrote = ok && slot < CAP;
-    if (wrote) qkeys[KLIST + slot] = key;
-    const int nw = __popc(__ballot_sync(0xffffffffu, wrote));
-    __syncwarp();
-    if (nw && lane == leader) {
-      __threadfence_block();
-      atomicAdd(&sel.done[q], nw);  // publish: nw more slots hold valid keys
-    }
-    mine = ok && !wrote;            // overflowed lanes retry after the flush
-    if (base + n < CAP) return;     // buffer not full
-    if (base < CAP) {
-      // this reservation filled the buffer: flush once every reserved slot has been written
-      while (*reinterpret_cast<volatile int*>(&sel.done[q]) < CAP) __nanosleep(20);
-      __threadfence_block();
+    const bool over = slot >= CAP;
+    if (__any_sync(0xffffffffu, slot == CAP - 1)) {
+      while (true) {
+        bool full = true;
+        for (int i = lane; i < CAP; i += 32) full &= *reinterpret_cast<volatile uint64_t*>(&qkeys[KLIST + i]) != 0ull;
+        if (__all_sync(0xffffffffu, full)) break;
+        __nanosleep(20);
+      }
       flush_query<KLIST, CAP>(qkeys, CAP, k, &sel.thr_key[q], lane);
+      for (int i = lane; i < CAP; i += 32) qkeys[KLIST + i] = 0ull;
+      __syncwarp();
       if (lane == 0) {
         const uint64_t t = sel.thr_key[q];
         sel.thr_f[q] = t ? key_score(t) : -INFINITY;
-        sel.done[q] = 0;
         __threadfence_block();
         *reinterpret_cast<volatile int*>(&sel.cnt[q]) = 0;  // reopens the buffer
       }
       __syncwarp();
-    } else {
-      // already full when this warp arrived: wait for the flushing warp to reopen it
-      while (*reinterpret_cast<volatile int*>(&sel.cnt[q]) >= CAP) __nanosleep(40);
-      __threadfence_block();
     }
+    if (!__any_sync(0xffffffffu, over)) return;
+    while (*reinterpret_cast<volatile int*>(&sel.cnt[q]) >= CAP) __nanosleep(40);
+    __threadfence_block();
+    slot = -1;
+    if (over && key > *reinterpret_cast<volatile uint64_t*>(&sel.thr_key[q])) {
+      slot = atomicAdd(&sel.cnt[q], 1);
+      if (slot < CAP) *reinterpret_cast<volatile uint64_t*>(&qkeys[KLIST + slot]) = key;
+    }
+    if (!__any_sync(0xffffffffu, slot >= CAP - 1)) return;
   }
 }
 
@@ -249,7 +240,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int ew = warp - 2;    // select-warp index 0..3 (query ownership for the final drain)
     const uint32_t q_mask = nq < kNQ ? (1u << nq) - 1u : 0xffffffffu;
-    const SelectorState sel{keys, thr_key, thr_f, cnt, done, bnd_key};
+    const SelectorState sel{keys, thr_key, thr_f, cnt, bnd_key};
 
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -290,13 +281,40 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
           }
         }
       }
-      // top-k candidates
+      // top-k candidates: every lane reserves its own slots (independent smem atomics, all in flight together),
+      // then stores; only reservations that hit the end of a buffer take the slow path.
       const uint32_t wm = __reduce_or_sync(0xffffffffu, pend_top);
       if (wm) {
+        int slot[kNQ];
 #pragma unroll
         for (int q = 0; q < kNQ; ++q) {
-          if ((wm >> q) & 1u)  // warp-uniform
-            push_candidates<KLIST, CAP>(sel, q, make_key(__uint_as_float(r[q]), uint32_t(row)), (pend_top >> q) & 1u, k, lane);
+          slot[q] = -1;
+          if ((wm >> q) & 1u) {
+            if ((pend_top >> q) & 1u) {
+              const uint64_t key = make_key(__uint_as_float(r[q]), uint32_t(row));
+              if (key < bnd_key[q] && key > *reinterpret_cast<volatile uint64_t*>(&thr_key[q])) slot[q] = atomicAdd(&cnt[q], 1);
+            }
+          }
+        }
+        uint32_t edge = 0;
+#pragma unroll
+        for (int q = 0; q < kNQ; ++q) {
+          if ((wm >> q) & 1u) {
+            if (slot[q] >= 0) {
+              if (slot[q] < CAP)
+                *reinterpret_cast<volatile uint64_t*>(&keys[q * L::kKeysPerQuery + KLIST + slot[q]]) =
+                    make_key(__uint_as_float(r[q]), uint32_t(row));
+              if (slot[q] >= CAP - 1) edge |= 1u << q;
+            }
+          }
+        }
+        const uint32_t we = __reduce_or_sync(0xffffffffu, edge);
+        if (we) {
+#pragma unroll
+          for (int q = 0; q < kNQ; ++q) {
+            if ((we >> q) & 1u)  // warp-uniform
+              resolve_full<KLIST, CAP>(sel, q, make_key(__uint_as_float(r[q]), uint32_t(row)), slot[q], k, lane);
+          }
         }
       }
     }
