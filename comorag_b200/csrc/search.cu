@@ -46,7 +46,8 @@ struct SearchLayout {
            + kNQ * 4               // thr_f
            + kNQ * 4               // cnt
            + kNQ * 8 + kNQ * 4     // continuation bound (key, score)
-           + kNQ * 4 * 5           // done, running min, running max (+ slack)
+           + kNQ * 4               // admission floor
+           + 4 * kNQ * 2 * 4       // min/max cross-warp reduction
            + 16;                   // tmem base
   }
   __host__ static size_t smem_bytes(int num_kb) {
@@ -54,71 +55,12 @@ struct SearchLayout {
   }
 };
 
-// Shared selector state of one CTA (all pointers into shared memory).
-struct SelectorState {
-  uint64_t* keys;      // [kNQ][KLIST + CAP]
-  uint64_t* thr_key;   // [kNQ] current k-th best key (0 while fewer than k are held)
-  float* thr_f;        // [kNQ] its score (-inf while fewer than k are held)
-  int* cnt;            // [kNQ] candidate slots reserved since the last flush
-  const uint64_t* bnd_key;  // [kNQ] "search after" bound
-};
-
-// Slow path of the selector, entered by a whole warp for one query q when some lane's reservation hit the end of
-// the candidate buffer: slot == CAP-1 means "this lane's candidate filled the buffer" (exactly one lane in the CTA
-// per round), slot >= CAP means "arrived while it was full".  The filling warp waits until every reserved slot holds
-// a key (valid keys are non-zero, the region is zeroed after each flush), sorts, publishes the new threshold and
-// reopens the buffer; overflowed lanes then re-offer their candidate against the fresh threshold.
-// No CTA-wide barrier: a warp never blocks between reserving a slot and writing it, so the waits cannot cycle.
-template <int KLIST, int CAP>
-__device__ __noinline__ void resolve_full(const SelectorState sel, int q, uint64_t key, int slot, int k, int lane) {
-  uint64_t* qkeys = sel.keys + q * (KLIST + CAP);
-  while (true) {
-    const bool over = slot >= CAP;
-    if (__any_sync(0xffffffffu, slot == CAP - 1)) {
-      while (true) {
-        bool full = true;
-        for (int i = lane; i < CAP; i += 32) full &= *reinterpret_cast<volatile uint64_t*>(&qkeys[KLIST + i]) != 0ull;
-        if (__all_sync(0xffffffffu, full)) break;
-        __nanosleep(20);
-      }
-      flush_query<KLIST, CAP>(qkeys, CAP, k, &sel.thr_key[q], lane);
-      for (int i = lane; i < CAP; i += 32) qkeys[KLIST + i] = 0ull;
-      __syncwarp();
-      if (lane == 0) {
-        const uint64_t t = sel.thr_key[q];
-        sel.thr_f[q] = t ? key_score(t) : -INFINITY;
-        __threadfence_block();
-        *reinterpret_cast<volatile int*>(&sel.cnt[q]) = 0;  // reopens the buffer
-      }
-      __syncwarp();
-    }
-    if (!__any_sync(0xffffffffu, over)) return;
-    while (*reinterpret_cast<volatile int*>(&sel.cnt[q]) >= CAP) __nanosleep(40);
-    __threadfence_block();
-    slot = -1;
-    if (over && key > *reinterpret_cast<volatile uint64_t*>(&sel.thr_key[q])) {
-      slot = atomicAdd(&sel.cnt[q], 1);
-      if (slot < CAP) *reinterpret_cast<volatile uint64_t*>(&qkeys[KLIST + slot]) = key;
-    }
-    if (!__any_sync(0xffffffffu, slot >= CAP - 1)) return;
-  }
-}
-
-// float min/max on shared memory through the integer atomics (sign-split trick; works for mixed signs and +-inf)
-__device__ __forceinline__ void smem_atomic_min_f32(float* addr, float v) {
-  if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
-  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
-}
-__device__ __forceinline__ void smem_atomic_max_f32(float* addr, float v) {
-  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
-  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
-}
-
 template <int KLIST, int CAP, int STAGES>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_constant__ CUtensorMap tm_q,
                    int n_rows, int num_kb, int nq, int k, const uint64_t* __restrict__ after_keys,
-                   uint64_t* __restrict__ part_keys, float* __restrict__ part_minmax) {
+                   const float* __restrict__ thr_floor, int floor_stride, uint64_t* __restrict__ part_keys,
+                   float* __restrict__ part_minmax) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -134,12 +76,11 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   uint64_t* thr_key = bar_q + 1;              // [kNQ]
   float* thr_f = reinterpret_cast<float*>(thr_key + kNQ);  // [kNQ]
   int* cnt = reinterpret_cast<int*>(thr_f + kNQ);          // [kNQ]
-  int* done = cnt + kNQ;                                   // [kNQ] candidate slots already written
-  float* mn_f = reinterpret_cast<float*>(done + kNQ);      // [kNQ] running min over the CTA's rows
-  float* mx_f = mn_f + kNQ;                                // [kNQ] running max
-  uint64_t* bnd_key = reinterpret_cast<uint64_t*>(mx_f + kNQ + 2 * kNQ);  // [kNQ] admit only keys < bnd_key
+  float* red = reinterpret_cast<float*>(cnt + kNQ);        // [4][kNQ][2]
+  uint64_t* bnd_key = reinterpret_cast<uint64_t*>(red + 4 * kNQ * 2);  // [kNQ] admit only keys < bnd_key
   float* bnd_f = reinterpret_cast<float*>(bnd_key + kNQ);              // [kNQ] score part of the bound
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bnd_f + kNQ);
+  float* floor_f = bnd_f + kNQ;                                        // [kNQ] admission floor from the sample pre-pass
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(floor_f + kNQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -168,11 +109,13 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   for (int i = threadIdx.x; i < kNQ * L::kKeysPerQuery; i += kSearchThreads) keys[i] = 0ull;
   if (threadIdx.x < kNQ) {
     thr_key[threadIdx.x] = 0ull;
-    thr_f[threadIdx.x] = -INFINITY;
+    // A floor is a score that at least k rows of THIS shard are known to reach (the k-th best of a row sample, see
+    // crag_search_topk): nothing below it can be in the top-k, so the selector starts with a tight threshold
+    // instead of admitting every row of the first tiles.
+    const float fl = (thr_floor != nullptr && int(threadIdx.x) < nq) ? thr_floor[size_t(threadIdx.x) * floor_stride] : -INFINITY;
+    floor_f[threadIdx.x] = fl;
+    thr_f[threadIdx.x] = fl;
     cnt[threadIdx.x] = 0;
-    done[threadIdx.x] = 0;
-    mn_f[threadIdx.x] = INFINITY;
-    mx_f[threadIdx.x] = -INFINITY;
     // "search after": rank continuation for k > 128 -- only candidates strictly below the previous pass's last key
     const uint64_t b = (after_keys != nullptr && int(threadIdx.x) < nq) ? after_keys[threadIdx.x] : ~0ull;
     bnd_key[threadIdx.x] = b;
@@ -234,13 +177,11 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
     }
   } else {
     // ================================================================== select
-    // Each select warp runs at its own pace (no CTA-wide barrier per tile).  Per tile a thread only COMPARES its
-    // 32 scores against the query's admission threshold and running (min, max), all read from shared memory;
-    // the rare hits take the slow paths below.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int ew = warp - 2;    // select-warp index 0..3 (query ownership for the final drain)
-    const uint32_t q_mask = nq < kNQ ? (1u << nq) - 1u : 0xffffffffu;
-    const SelectorState sel{keys, thr_key, thr_f, cnt, bnd_key};
+    const int ew = warp - 2;    // select-warp index 0..3 (query ownership for flushes)
+    float mn[kNQ], mx[kNQ];
+#pragma unroll
+    for (int q = 0; q < kNQ; ++q) { mn[q] = INFINITY; mx[q] = -INFINITY; }
 
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -256,64 +197,49 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
 
       const int row = tile * kTileRows + quad * 32 + lane;
-      uint32_t pend_top = 0, pend_mm = 0;
+      uint32_t pending = 0;
       if (row < n_rows) {
 #pragma unroll
         for (int q = 0; q < kNQ; ++q) {
           const float s = __uint_as_float(r[q]);
-          if (s >= thr_f[q] && s <= bnd_f[q]) pend_top |= 1u << q;
-          if (s < mn_f[q] || s > mx_f[q]) pend_mm |= 1u << q;
+          mn[q] = fminf(mn[q], s);
+          mx[q] = fmaxf(mx[q], s);
+          if (s >= thr_f[q] && s <= bnd_f[q]) pending |= 1u << q;
         }
-        pend_top &= q_mask;
-        pend_mm &= q_mask;
+        if (nq < kNQ) pending &= (1u << nq) - 1u;
       }
-      // running (min, max): a new extreme is a 1/i event for the i-th row -> a handful of smem atomics per query
-      const uint32_t wm_mm = __reduce_or_sync(0xffffffffu, pend_mm);
-      if (wm_mm) {
+      while (true) {
+        bool want_flush = false;
 #pragma unroll
         for (int q = 0; q < kNQ; ++q) {
-          if ((wm_mm >> q) & 1u) {
-            if ((pend_mm >> q) & 1u) {
-              const float s = __uint_as_float(r[q]);
-              smem_atomic_min_f32(&mn_f[q], s);
-              smem_atomic_max_f32(&mx_f[q], s);
+          if (((pending >> q) & 1u) && make_key(__uint_as_float(r[q]), uint32_t(row)) >= bnd_key[q]) pending &= ~(1u << q);
+          if ((pending >> q) & 1u) {
+            const int slot = atomicAdd(&cnt[q], 1);
+            if (slot < CAP) {
+              keys[q * L::kKeysPerQuery + KLIST + slot] = make_key(__uint_as_float(r[q]), uint32_t(row));
+              pending &= ~(1u << q);
+            }
+            if (slot >= CAP - 1) want_flush = true;
+          }
+        }
+        if (!named_bar_or(1, kEpiThreads, want_flush || pending != 0)) break;
+        for (int q = ew; q < kNQ; q += 4) {
+          const int c = cnt[q];
+          if (c >= CAP) {
+            flush_query<KLIST, CAP>(keys + q * L::kKeysPerQuery, CAP, k, &thr_key[q], lane);
+            if (lane == 0) {
+              const uint64_t t = thr_key[q];
+              thr_f[q] = fmaxf(floor_f[q], t ? key_score(t) : -INFINITY);
+              cnt[q] = 0;
             }
           }
         }
-      }
-      // top-k candidates: every lane reserves its own slots (independent smem atomics, all in flight together),
-      // then stores; only reservations that hit the end of a buffer take the slow path.
-      const uint32_t wm = __reduce_or_sync(0xffffffffu, pend_top);
-      if (wm) {
-        int slot[kNQ];
-#pragma unroll
-        for (int q = 0; q < kNQ; ++q) {
-          slot[q] = -1;
-          if ((wm >> q) & 1u) {
-            if ((pend_top >> q) & 1u) {
-              const uint64_t key = make_key(__uint_as_float(r[q]), uint32_t(row));
-              if (key < bnd_key[q] && key > *reinterpret_cast<volatile uint64_t*>(&thr_key[q])) slot[q] = atomicAdd(&cnt[q], 1);
-            }
-          }
-        }
-        uint32_t edge = 0;
-#pragma unroll
-        for (int q = 0; q < kNQ; ++q) {
-          if ((wm >> q) & 1u) {
-            if (slot[q] >= 0) {
-              if (slot[q] < CAP)
-                *reinterpret_cast<volatile uint64_t*>(&keys[q * L::kKeysPerQuery + KLIST + slot[q]]) =
-                    make_key(__uint_as_float(r[q]), uint32_t(row));
-              if (slot[q] >= CAP - 1) edge |= 1u << q;
-            }
-          }
-        }
-        const uint32_t we = __reduce_or_sync(0xffffffffu, edge);
-        if (we) {
+        named_bar_sync(1, kEpiThreads);
+        if (pending) {
 #pragma unroll
           for (int q = 0; q < kNQ; ++q) {
-            if ((we >> q) & 1u)  // warp-uniform
-              resolve_full<KLIST, CAP>(sel, q, make_key(__uint_as_float(r[q]), uint32_t(row)), slot[q], k, lane);
+            if (((pending >> q) & 1u) && make_key(__uint_as_float(r[q]), uint32_t(row)) < thr_key[q])
+              pending &= ~(1u << q);
           }
         }
       }
@@ -328,9 +254,29 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       uint64_t* dst = part_keys + (size_t(blockIdx.x) * kNQ + q) * k;
       for (int j = lane; j < k; j += 32) dst[j] = keys[q * L::kKeysPerQuery + j];
     }
+#pragma unroll
+    for (int q = 0; q < kNQ; ++q) {
+      float a = mn[q], b = mx[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+      }
+      if (lane == q) {
+        red[(ew * kNQ + q) * 2 + 0] = a;
+        red[(ew * kNQ + q) * 2 + 1] = b;
+      }
+    }
+    named_bar_sync(1, kEpiThreads);
     if (ew == 0) {
-      part_minmax[(size_t(blockIdx.x) * kNQ + lane) * 2 + 0] = mn_f[lane];
-      part_minmax[(size_t(blockIdx.x) * kNQ + lane) * 2 + 1] = mx_f[lane];
+      float a = red[lane * 2], b = red[lane * 2 + 1];
+#pragma unroll
+      for (int w = 1; w < 4; ++w) {
+        a = fminf(a, red[(w * kNQ + lane) * 2]);
+        b = fmaxf(b, red[(w * kNQ + lane) * 2 + 1]);
+      }
+      part_minmax[(size_t(blockIdx.x) * kNQ + lane) * 2 + 0] = a;
+      part_minmax[(size_t(blockIdx.x) * kNQ + lane) * 2 + 1] = b;
     }
   }
 
@@ -468,6 +414,7 @@ struct SearchPlan {
   int grid;
   size_t keys_bytes;    // per 32-query pass
   size_t minmax_bytes;  // per 32-query pass
+  size_t sample_bytes;  // ids + scores of the sample pre-pass (one 32-query pass)
 };
 
 SearchPlan plan_search(int k) {
@@ -476,17 +423,20 @@ SearchPlan plan_search(int k) {
   if (p.grid <= 0) p.grid = 148;
   p.keys_bytes = ((size_t(p.grid) * kNQ * k * 8) + 255) & ~size_t(255);
   p.minmax_bytes = ((size_t(p.grid) * kNQ * 2 * 4) + 255) & ~size_t(255);
+  p.sample_bytes = ((size_t(kNQ) * k * (8 + 4)) + 255) & ~size_t(255);
   return p;
 }
 
 template <int KLIST, int CAP, int STAGES>
 int launch_search(const CUtensorMap& tm_corpus, const CUtensorMap& tm_q, int n_rows, int num_kb, int nq, int k,
-                  int grid, const uint64_t* after_keys, uint64_t* part_keys, float* part_minmax, cudaStream_t stream) {
+                  int grid, const uint64_t* after_keys, const float* thr_floor, int floor_stride, uint64_t* part_keys,
+                  float* part_minmax, cudaStream_t stream) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   const size_t smem = L::smem_bytes(num_kb);
   auto kern = search_topk_kernel<KLIST, CAP, STAGES>;
   CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, n_rows, num_kb, nq, k, after_keys, part_keys, part_minmax);
+  kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, n_rows, num_kb, nq, k, after_keys, thr_floor, floor_stride,
+                                               part_keys, part_minmax);
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }
@@ -500,7 +450,7 @@ extern "C" size_t crag_search_workspace_bytes(int nq, int k) {
   (void)nq;
   if (k < 1 || k > 128) return 0;
   const SearchPlan p = plan_search(k);
-  return p.keys_bytes + p.minmax_bytes;
+  return p.keys_bytes + p.minmax_bytes + p.sample_bytes;
 }
 
 namespace crag {
@@ -526,7 +476,8 @@ inline int scan_grid(int64_t n_rows, const SearchPlan& plan) {
 
 // one corpus pass for <= 32 queries: per-CTA partial lists into the workspace
 int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride, const void* queries, int nq,
-              int k, const uint64_t* after_keys, void* workspace, const SearchPlan& plan, cudaStream_t stream) {
+              int k, const uint64_t* after_keys, const float* thr_floor, int floor_stride, void* workspace,
+              const SearchPlan& plan, cudaStream_t stream) {
   const int grid = scan_grid(n_rows, plan);
   if (grid == 0) return CRAG_OK;
   uint64_t* part_keys = static_cast<uint64_t*>(workspace);
@@ -537,12 +488,8 @@ int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_st
   rc = make_tmap_bf16_2d(&tm_q, queries, uint64_t(nq), uint64_t(dim), uint64_t(dim) * 2, kNQ);
   if (rc != CRAG_OK) return rc;
   const int num_kb = dim / kBlockK;
-  // small candidate buffers keep the admission thresholds fresh (a threshold only moves when a buffer is flushed)
-  // and make a flush a 32- or 64-key sort; the smem they free goes to TMA stages
-  if (k <= 16) return launch_search<16, 16, 9>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, part_keys, part_minmax, stream);
-  if (k <= 32) return launch_search<32, 32, 8>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, part_keys, part_minmax, stream);
-  if (k <= 64) return launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, part_keys, part_minmax, stream);
-  return launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, part_keys, part_minmax, stream);
+  if (k <= 64) return launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
+  return launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
 }
 
 // merge the per-CTA partials of one pass into the final (ids, scores, minmax) of its <= 32 queries
@@ -572,7 +519,7 @@ extern "C" int crag_search_scan(const void* corpus, int64_t n_rows, int dim, int
   int rc = check_search_args(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, workspace, workspace_bytes, plan);
   if (rc != CRAG_OK) return rc;
   if (nq > kNQ) return fail(CRAG_ERR_INVALID, "crag_search_scan handles one pass of at most %d queries (nq=%d)", kNQ, nq);
-  return scan_pass(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, nullptr, workspace, plan, static_cast<cudaStream_t>(stream));
+  return scan_pass(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, nullptr, nullptr, 0, workspace, plan, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int crag_search_finalize(const void* workspace, size_t workspace_bytes, int64_t n_rows, int nq, int k,
@@ -595,11 +542,29 @@ extern "C" int crag_search_topk_after(const void* corpus, int64_t n_rows, int di
   int rc = check_search_args(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, workspace, workspace_bytes, plan);
   if (rc != CRAG_OK) return rc;
   if (!out_ids || !out_scores) return fail(CRAG_ERR_INVALID, "search: null output pointer");
+  // Sample pre-pass (first-rank searches over big shards only): score every `stride`-th row -- one tile per CTA --
+  // and take the sample's k-th best score as the admission floor of the full scan.  The sample rows are rows of the
+  // shard, so at least k rows reach the floor and nothing below it can rank in the top-k; the full scan then admits
+  // ~k * stride candidates per query in total instead of treating the head of every CTA's stream as candidates.
+  const int64_t sample_rows = int64_t(plan.grid) * kTileRows;
+  const int64_t sample_stride = n_rows / sample_rows;
+  const bool use_sample = after_keys == nullptr && sample_stride >= 16 &&
+                          workspace_bytes >= plan.keys_bytes + plan.minmax_bytes + plan.sample_bytes;
+  int64_t* sample_ids = reinterpret_cast<int64_t*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes + plan.minmax_bytes);
+  float* sample_scores = reinterpret_cast<float*>(sample_ids + size_t(kNQ) * k);
   for (int q0 = 0; q0 < nq; q0 += kNQ) {
     const int nqc = (nq - q0) < kNQ ? (nq - q0) : kNQ;
-    rc = scan_pass(corpus, n_rows, dim, corpus_row_stride, static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2, nqc, k,
-                   after_keys ? after_keys + q0 : nullptr, workspace, plan, stream);
-    if (rc != CRAG_OK) return rc;
+    const uint8_t* qptr = static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2;
+    const float* floor = nullptr;
+    if (use_sample) {
+      rc = scan_pass(corpus, sample_rows, dim, corpus_row_stride * sample_stride, qptr, nqc, k, nullptr, nullptr, 0, workspace, plan, stream);
+      if (rc != CRAG_OK) return rc;
+      rc = finalize_pass(workspace, sample_rows, nqc, k, 0, sample_ids, sample_scores, nullptr, nullptr, plan, stream);
+      if (rc != CRAG_OK) return rc;
+      floor = sample_scores + (k - 1);   // k-th best sample score of query q at floor[q * k]; -inf if the sample is short
+    }
+    rc = scan_pass(corpus, n_rows, dim, corpus_row_stride, qptr, nqc, k, after_keys ? after_keys + q0 : nullptr, floor, k,
+                   workspace, plan, stream);
     rc = finalize_pass(workspace, n_rows, nqc, k, row_offset, out_ids + size_t(q0) * k, out_scores + size_t(q0) * k,
                        out_minmax ? out_minmax + size_t(q0) * 2 : nullptr, last_keys ? last_keys + q0 : nullptr, plan, stream);
     if (rc != CRAG_OK) return rc;

@@ -42,9 +42,14 @@ def main():
                 for f in fns: f()
             e1.record(); torch.cuda.synchronize()
             return e0.elapsed_time(e1) / reps * 1e3
-        t_scan, t_both = timeit([scan]), timeit([scan, fin])
+        oi = torch.empty(nq, k, dtype=torch.int64, device=dev); osc = torch.empty(nq, k, device=dev); omm = torch.empty(nq, 2, device=dev)
+
+        def full():
+            _native.check(lib.crag_search_topk(corpus.data_ptr(), rows, dim, dim, 0, q.data_ptr(), nq, k, oi.data_ptr(), osc.data_ptr(),
+                                               omm.data_ptr(), ws.data_ptr(), ws_bytes, st.cuda_stream), "topk")
+        t_scan, t_both, t_full = timeit([scan]), timeit([scan, fin]), timeit([full])
         ideal = rows * dim * 2 / 7.15e12 * 1e6
-        out.append({"rows": rows, "scan_us": round(t_scan, 1), "scan+finalize_us": round(t_both, 1), "ideal_us@7.15TB/s": round(ideal, 1),
+        out.append({"rows": rows, "scan_us": round(t_scan, 1), "scan+finalize_us": round(t_both, 1), "topk_us(sampled)": round(t_full, 1), "ideal_us@7.15TB/s": round(ideal, 1),
                     "overhead_us": round(t_both - ideal, 1)})
         print(json.dumps(out[-1]), flush=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"time_search_k{k}_nq{nq}.json"), "w"), indent=1)
