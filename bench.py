@@ -410,7 +410,9 @@ def run_ours(args):
                 encode["cpu_baseline"] = {"unavailable": repr(e)[:200]}
 
     if rank == 0:
-        launches_per_step = 2 + (1 if world > 1 else 0)  # scan + per-shard merge (+ cross-rank merge)
+        # sample-floor scan + its merge, full scan + per-shard merge (+ cross-rank merge of the all-gathered records)
+        sampled = args.nq * args.k >= 128 and my_rows // (lib.crag_sm_count() * 128) >= 16
+        launches_per_step = (4 if sampled else 2) + (1 if world > 1 else 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
