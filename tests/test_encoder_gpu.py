@@ -197,3 +197,55 @@ def test_cinderella_plumbing_top10_matches_reference_math(dev, gold, tmp_path):
             j += 1
         assert set(ids[qi].tolist()) <= set(range(len(store.hash_ids)))
         assert np.abs(np.sort(scores[qi]) - np.sort(raw[ids[qi]])).max() < 3e-2
+
+
+def test_xlm_roberta_variant_position_offset(dev):
+    """XLM-R style checkpoints (position offset 2, eps 1e-5, one token type) through the same kernels."""
+    from comorag_b200.encoder import BertEncoderB200, EncoderConfig, random_state_dict
+    cfg = EncoderConfig(128, 2, 2, 256, 1000, max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5, position_offset=2)
+    sd = random_state_dict(cfg, seed=5, std=0.06, device=dev)
+    enc = BertEncoderB200(cfg, sd, dev)
+    g = torch.Generator().manual_seed(2)
+    seqs = [[0] + torch.randint(5, 1000, (n,), generator=g).tolist() + [2] for n in (3, 100, 510)]
+    out = enc.encode_token_lists(seqs)
+    sd_q = {k: (v.bfloat16().float() if v.dim() == 2 else v) for k, v in sd.items()}
+    ref = eo.encode_token_lists(sd_q, cfg, seqs, pad_id=1)
+    assert float(torch.nn.functional.cosine_similarity(out, ref, dim=1).min()) > 0.999 and float((out - ref).abs().max()) < 1e-2
+    with pytest.raises(Exception):
+        enc.encode_token_lists([[0] * 600])          # longer than the position table: reported, not truncated silently
+
+
+def test_sixteen_threads_share_the_engine(dev, gold, tmp_path):
+    """ComoRAG answers questions from a 16-thread pool (ComoRAG.py:436-441): concurrent batch_encode / store.search
+    calls (with and without the request coalescer) return exactly what serial calls return."""
+    from concurrent.futures import ThreadPoolExecutor
+    from comorag_b200.config import EngineConfig
+    from comorag_b200.embedding_model import BGEEmbeddingModel
+    from comorag_b200.embedding_store import EmbeddingStore
+    texts = gold["texts"].tolist()
+    queries = [f"{t[:40]} {i}" for i, t in enumerate(texts * 3)]
+    for coalesce in (False, True):
+        cfg = EngineConfig(embedding_model_name=CKPT, embedding_batch_size=8, embedding_max_seq_len=512, embedding_coalesce=coalesce)
+        model = BGEEmbeddingModel(global_config=cfg, embedding_model_name=CKPT)
+        store = EmbeddingStore(model, str(tmp_path / f"s{int(coalesce)}"), 8, "chunk")
+        store.insert_strings(texts)
+        serial_e = [model.batch_encode(q) for q in queries]
+        serial_s = [store.search(e, 5) for e in serial_e]
+
+        def work(i):
+            e = model.batch_encode(queries[i])
+            return e, store.search(e, 5)
+
+        with ThreadPoolExecutor(16) as ex:
+            par = list(ex.map(work, range(len(queries))))
+        for i, (e, (ids, sc, mm)) in enumerate(par):
+            np.testing.assert_allclose(e, serial_e[i], atol=1e-6)
+            np.testing.assert_allclose(sc, serial_s[i][1], atol=1e-5)
+            ref_ids, ref_sc = serial_s[i][0][0], serial_s[i][1][0]
+            for j in range(5):  # ranks whose neighbours are further than the batching noise must agree exactly
+                lo = ref_sc[j] - ref_sc[j + 1] if j + 1 < 5 else 1.0
+                hi = ref_sc[j - 1] - ref_sc[j] if j > 0 else 1.0
+                if min(lo, hi) > 1e-4:
+                    assert ids[0][j] == ref_ids[j]
+        if coalesce:
+            assert model._coalescer.stats["forwards"] < len(queries)      # requests really shared launches

@@ -51,3 +51,27 @@ def test_padding_does_not_change_a_row(model):
     a = eo.encode_token_lists(sd, cfg, [[2, 10, 11, 12, 3]])
     b = eo.encode_token_lists(sd, cfg, [[2, 10, 11, 12, 3], [2] + list(range(5, 200)) + [3]])
     assert torch.allclose(a[0], b[0], atol=1e-6)
+
+
+def test_oracle_matches_hf_xlm_roberta_positions():
+    """XLM-R family (bge-m3 / bge-reranker backbones): position ids start at padding_idx + 1 = 2 and there is one
+    token type.  The oracle with position_offset=2 equals HF's XLMRobertaModel on a random small checkpoint."""
+    from transformers import XLMRobertaConfig, XLMRobertaModel
+    hf_cfg = XLMRobertaConfig(vocab_size=300, hidden_size=64, num_hidden_layers=2, num_attention_heads=2, intermediate_size=128,
+                              max_position_embeddings=130, type_vocab_size=1, pad_token_id=1, layer_norm_eps=1e-5)
+    torch.manual_seed(3)
+    hf = XLMRobertaModel(hf_cfg, add_pooling_layer=False).eval()
+    sd = {k: v for k, v in hf.state_dict().items()}
+    cfg = EncoderConfig(64, 2, 2, 128, 300, max_position_embeddings=130, type_vocab_size=1, layer_norm_eps=1e-5, position_offset=2)
+    seqs = [[0, 17, 45, 99, 2], [0] + list(range(10, 60)) + [2]]
+    got = eo.encode_token_lists(sd, cfg, seqs, pad_id=1)
+    L = max(len(s) for s in seqs)
+    ids = torch.full((2, L), 1, dtype=torch.long)
+    mask = torch.zeros((2, L), dtype=torch.long)
+    for i, s_ in enumerate(seqs):
+        ids[i, :len(s_)] = torch.tensor(s_)
+        mask[i, :len(s_)] = 1
+    with torch.no_grad():
+        out = hf(input_ids=ids, attention_mask=mask).last_hidden_state
+    want = torch.nn.functional.normalize(eo.mean_pooling(out, mask), dim=1)
+    assert float((got - want).abs().max()) < 2e-6
