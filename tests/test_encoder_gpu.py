@@ -232,6 +232,8 @@ def test_sixteen_threads_share_the_engine(dev, gold, tmp_path):
         serial_e = [model.batch_encode(q) for q in queries]
         serial_s = [store.search(e, 5) for e in serial_e]
 
+        before = model._coalescer.stats["forwards"] if coalesce else 0
+
         def work(i):
             e = model.batch_encode(queries[i])
             return e, store.search(e, 5)
@@ -248,4 +250,4 @@ def test_sixteen_threads_share_the_engine(dev, gold, tmp_path):
                 if min(lo, hi) > 1e-4:
                     assert ids[0][j] == ref_ids[j]
         if coalesce:
-            assert model._coalescer.stats["forwards"] < len(queries)      # requests really shared launches
+            assert model._coalescer.stats["forwards"] - before < len(queries)      # requests really shared launches
