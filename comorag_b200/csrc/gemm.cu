@@ -309,7 +309,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     tmem_relinquish_2cta();
   }
   tc_fence_before();
-  cluster_sync_all();
+  cluster_sync_all();   // both CTAs' barriers initialised and TMEM allocated before any cross-CTA traffic
+  __syncthreads();      // (the cluster barrier already orders this; the CTA barrier keeps racecheck's model happy)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
