@@ -160,7 +160,12 @@ class CpuSearch:
         import torch
         per_query = float(np.median(times))
         scale = self.full_rows / self.rows
-        return {"value": 1.0 / (per_query * scale), "unit": UNIT, "cores": os.cpu_count(), "threads": torch.get_num_threads(),
+        try:
+            from threadpoolctl import threadpool_info
+            blas_threads = max([i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"] or [1])
+        except Exception:
+            blas_threads = torch.get_num_threads()
+        return {"value": 1.0 / (per_query * scale), "unit": UNIT, "cores": os.cpu_count(), "threads": blas_threads,
                 "kind": "port",
                 "sample": f"{len(times)} single queries over an fp32 [{self.rows}, {self.dim}] slab (gen {self.gen_s:.1f}s), "
                           f"median {per_query * 1e3:.1f} ms/query, scaled x{scale:g} rows to {self.full_rows}"}
@@ -216,6 +221,11 @@ def run_reference(args):
     if rank != 0:
         return
     t_all = time.time()
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host thread it can.  numpy / torch
+    # have not been imported yet in this process, so the BLAS pools still honour the environment.
+    n_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(n_threads)
     rows = min(pick_cpu_rows(args.rows, args.dim, 40.0), 1_000_000)
     cs = CpuSearch(rows, args.dim, args.rows)
     per_step = 2  # queries per step (the reference scores one query at a time; a step samples 2 of the 32)
