@@ -50,6 +50,58 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(half_x, copysignf(erf_abs, z), half_x);  // 0.5 x (1 + erf(z))
 }
 
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): two lanes per instruction, which halves the FMA-pipe
+// instruction count of the GELU polynomial in the issue-bound FFN-up epilogue.
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_splat(float a) { return f2_pack(a, a); }
+
+// gelu_erf on a pair (same A&S 7.1.26 erf as the scalar version)
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t z = f2_mul(x, f2_splat(0.70710678118654752f));
+  float z0, z1;
+  f2_unpack(z, z0, z1);
+  const uint64_t az = f2_pack(fabsf(z0), fabsf(z1));
+  float d0, d1;
+  f2_unpack(f2_fma(az, f2_splat(0.3275911f), f2_splat(1.0f)), d0, d1);
+  float t0, t1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = f2_pack(t0, t1);
+  uint64_t p = f2_fma(f2_splat(1.061405429f), t, f2_splat(-1.453152027f));
+  p = f2_fma(p, t, f2_splat(1.421413741f));
+  p = f2_fma(p, t, f2_splat(-0.284496736f));
+  p = f2_fma(p, t, f2_splat(0.254829592f));
+  p = f2_mul(p, t);
+  float a0, a1;
+  f2_unpack(f2_mul(f2_mul(az, az), f2_splat(-1.4426950408889634f)), a0, a1);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  // erf(|z|) = 1 - p * e ; result = 0.5 x (1 + sign(z) erf(|z|))
+  float r0, r1;
+  f2_unpack(f2_fma(f2_mul(p, f2_splat(-1.0f)), f2_pack(e0, e1), f2_splat(1.0f)), r0, r1);
+  const uint64_t half_x = f2_mul(x, f2_splat(0.5f));
+  f2_unpack(f2_fma(half_x, f2_pack(copysignf(r0, z0), copysignf(r1, z1)), half_x), x0, x1);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -81,7 +133,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
       x[7] = __uint_as_float(r[v * 8 + 7]) + b1.w;
       if (EPI == GEMM_EPI_BIAS_GELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+        for (int j = 0; j < 8; j += 2) gelu_erf2(x[j], x[j + 1]);
       }
       if (EPI == GEMM_EPI_BIAS_RESIDUAL) {
         const uint4 rv = *reinterpret_cast<const uint4*>(rrow + v * 8);
