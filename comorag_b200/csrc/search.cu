@@ -488,6 +488,9 @@ int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_st
   rc = make_tmap_bf16_2d(&tm_q, queries, uint64_t(nq), uint64_t(dim), uint64_t(dim) * 2, kNQ);
   if (rc != CRAG_OK) return rc;
   const int num_kb = dim / kBlockK;
+  // small selectors (32- / 64-key sorts, one or two more TMA stages) once the admission floor keeps candidates rare
+  if (k <= 16 && thr_floor != nullptr) return launch_search<16, 16, 9>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
+  if (k <= 32 && thr_floor != nullptr) return launch_search<32, 32, 8>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
   if (k <= 64) return launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
   return launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
 }
