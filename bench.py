@@ -421,7 +421,8 @@ def run_ours(args):
 
     if rank == 0:
         # sample-floor scan + its merge, full scan + per-shard merge (+ cross-rank merge of the all-gathered records)
-        sampled = args.nq * args.k >= 128 and my_rows // (lib.crag_sm_count() * 128) >= 16
+        sampled = (args.nq * args.k >= 128 and my_rows // (lib.crag_sm_count() * 128) >= 16
+                   and (my_rows <= 2_000_000 or args.k >= 32))
         launches_per_step = (4 if sampled else 2) + (1 if world > 1 else 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -553,7 +553,9 @@ extern "C" int crag_search_topk_after(const void* corpus, int64_t n_rows, int di
   // itself costs ~40 us, so it is skipped for small query-block x k products and small shards.
   const int64_t sample_rows = int64_t(plan.grid) * kTileRows;
   const int64_t sample_stride = n_rows / sample_rows;
+  // pays off when the selector work is a visible share of the pass: small shards (multi-GPU strong scaling) or big k
   const bool use_sample = after_keys == nullptr && sample_stride >= 16 && int64_t(nq < kNQ ? nq : kNQ) * k >= 128 &&
+                          (n_rows <= 2000000 || k >= 32) &&
                           workspace_bytes >= plan.keys_bytes + plan.minmax_bytes + plan.sample_bytes;
   int64_t* sample_ids = reinterpret_cast<int64_t*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes + plan.minmax_bytes);
   float* sample_scores = reinterpret_cast<float*>(sample_ids + size_t(kNQ) * k);
