@@ -300,18 +300,28 @@ __device__ __forceinline__ void select_stream(uint64_t* keys, uint64_t* thr_slot
   if (lane == 0) *thr_slot = 0ull;
   __syncwarp();
   int c = 0;
-  for (int base = 0; base < total; base += 32) {
-    const int idx = base + lane;
-    const uint64_t key = idx < total ? fetch(idx) : 0ull;
-    const uint64_t thr = *thr_slot > bound ? *thr_slot : bound;
-    const bool take = key != 0 && key >= thr;
-    const uint32_t m = __ballot_sync(0xffffffffu, take);
-    if (take) keys[KLIST + c + __popc(m & ((1u << lane) - 1u))] = key;
-    c += __popc(m);
-    __syncwarp();
-    if (c + 32 > CAP) {
-      flush_query<KLIST, CAP>(keys, c, k, thr_slot, lane);
-      c = 0;
+  constexpr int U = 8;  // batches fetched ahead: the candidate lists live in L2, so the loads are issued 8 deep
+  for (int base0 = 0; base0 < total; base0 += 32 * U) {
+    uint64_t pre[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base0 + u * 32 + lane;
+      pre[u] = idx < total ? fetch(idx) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base0 + u * 32 >= total) break;
+      const uint64_t key = pre[u];
+      const uint64_t thr = *thr_slot > bound ? *thr_slot : bound;
+      const bool take = key != 0 && key >= thr;
+      const uint32_t m = __ballot_sync(0xffffffffu, take);
+      if (take) keys[KLIST + c + __popc(m & ((1u << lane) - 1u))] = key;
+      c += __popc(m);
+      __syncwarp();
+      if (c + 32 > CAP) {
+        flush_query<KLIST, CAP>(keys, c, k, thr_slot, lane);
+        c = 0;
+      }
     }
   }
   if (c > 0) flush_query<KLIST, CAP>(keys, c, k, thr_slot, lane);
@@ -477,7 +487,7 @@ inline int scan_grid(int64_t n_rows, const SearchPlan& plan) {
 // one corpus pass for <= 32 queries: per-CTA partial lists into the workspace
 int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride, const void* queries, int nq,
               int k, const uint64_t* after_keys, const float* thr_floor, int floor_stride, void* workspace,
-              const SearchPlan& plan, cudaStream_t stream) {
+              const SearchPlan& plan, cudaStream_t stream, bool small_selector = false) {
   const int grid = scan_grid(n_rows, plan);
   if (grid == 0) return CRAG_OK;
   uint64_t* part_keys = static_cast<uint64_t*>(workspace);
@@ -489,8 +499,8 @@ int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_st
   if (rc != CRAG_OK) return rc;
   const int num_kb = dim / kBlockK;
   // small selectors (32- / 64-key sorts, one or two more TMA stages) once the admission floor keeps candidates rare
-  if (k <= 16 && thr_floor != nullptr) return launch_search<16, 16, 9>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
-  if (k <= 32 && thr_floor != nullptr) return launch_search<32, 32, 8>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
+  if (k <= 16 && (thr_floor != nullptr || small_selector)) return launch_search<16, 16, 9>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
+  if (k <= 32 && (thr_floor != nullptr || small_selector)) return launch_search<32, 32, 8>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
   if (k <= 64) return launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
   return launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
 }
@@ -564,7 +574,8 @@ extern "C" int crag_search_topk_after(const void* corpus, int64_t n_rows, int di
     const uint8_t* qptr = static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2;
     const float* floor = nullptr;
     if (use_sample) {
-      rc = scan_pass(corpus, sample_rows, dim, corpus_row_stride * sample_stride, qptr, nqc, k, nullptr, nullptr, 0, workspace, plan, stream);
+      rc = scan_pass(corpus, sample_rows, dim, corpus_row_stride * sample_stride, qptr, nqc, k, nullptr, nullptr, 0, workspace, plan, stream,
+                     /*small_selector=*/true);   // one tile per CTA: cheap 32-/64-key sorts beat fresh thresholds
       if (rc != CRAG_OK) return rc;
       rc = finalize_pass(workspace, sample_rows, nqc, k, 0, sample_ids, sample_scores, nullptr, nullptr, plan, stream);
       if (rc != CRAG_OK) return rc;
