@@ -183,6 +183,8 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
 #pragma unroll
     for (int q = 0; q < kNQ; ++q) { mn[q] = INFINITY; mx[q] = -INFINITY; }
 
+    // direct first tile needs room for 128 keys per query and no admission bound of any kind
+    const bool direct_first = (KLIST + CAP >= 128) && thr_floor == nullptr && after_keys == nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -207,6 +209,25 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
           if (s >= thr_f[q] && s <= bnd_f[q]) pending |= 1u << q;
         }
         if (nq < kNQ) pending &= (1u << nq) - 1u;
+      }
+      // First tile of an unseeded pass: the lists are empty and every row is a candidate.  Skip the reservation
+      // protocol (128-way contended atomics, several flush rounds): each row's key goes straight to slot
+      // row_in_tile of the query's buffer and one 128-key sort per query builds the list.
+      if (direct_first && tile == int(blockIdx.x)) {
+#pragma unroll
+        for (int q = 0; q < kNQ; ++q)
+          keys[q * L::kKeysPerQuery + quad * 32 + lane] =
+              ((pending >> q) & 1u) ? make_key(__uint_as_float(r[q]), uint32_t(row)) : 0ull;
+        named_bar_sync(1, kEpiThreads);
+        for (int q = ew; q < kNQ; q += 4) {
+          flush_query<KLIST, CAP>(keys + q * L::kKeysPerQuery, 128 - KLIST, k, &thr_key[q], lane);
+          if (lane == 0) {
+            const uint64_t t = thr_key[q];
+            thr_f[q] = fmaxf(floor_f[q], t ? key_score(t) : -INFINITY);
+          }
+        }
+        named_bar_sync(1, kEpiThreads);
+        continue;
       }
       while (true) {
         bool want_flush = false;
@@ -568,7 +589,7 @@ extern "C" int crag_search_topk_after(const void* corpus, int64_t n_rows, int di
     const float* floor = nullptr;
     if (use_sample) {
       rc = scan_pass(corpus, sample_rows, dim, corpus_row_stride, qptr, nqc, k, nullptr, nullptr, 0, workspace, plan, stream,
-                     /*small_selector=*/true);   // one tile per CTA: cheap 32-/64-key sorts
+                     /*small_selector=*/false);  // one tile per CTA: the direct first-tile path of the 128-slot selector
       if (rc != CRAG_OK) return rc;
       rc = finalize_pass(workspace, sample_rows, nqc, k, 0, sample_ids, sample_scores, nullptr, nullptr, plan, stream);
       if (rc != CRAG_OK) return rc;
