@@ -13,6 +13,8 @@ import numpy as np
 
 from .index import DenseIndex, MAX_K
 
+FULL_RANKING_PAGED_MAX = 32768   # up to this many rows a full permutation is served by rank-continuation passes
+
 
 def min_max_normalize(x: np.ndarray) -> np.ndarray:
     """misc_utils.py:141-150."""
@@ -43,14 +45,23 @@ def dense_topk(index: DenseIndex, query_embeddings, k: int) -> Tuple[np.ndarray,
 def dense_passage_retrieval(index: DenseIndex, query_embedding, top_k: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
     """ComoRAG.py:950-967 for one query embedding [1, D] or [D].
 
-    top_k=None keeps the reference contract (a permutation of ALL rows + all normalised scores): scores for
-    every row are produced on the device in one pass and sorted there.  With top_k only the first top_k ranks
-    are produced by the fused kernel.
+    top_k=None keeps the reference contract (a permutation of ALL rows + all normalised scores): up to
+    FULL_RANKING_PAGED_MAX rows it is produced by the fused kernel alone (rank continuation, 128 ranks per pass);
+    beyond that all N scores are computed and sorted on the device.  With top_k only the first top_k ranks are
+    produced (what tri_retrieve actually consumes, ComoRAG.py:499,516).
     """
     import torch
     if top_k is not None:
         ids, sc = dense_topk(index, query_embedding, top_k)
         return ids[0], sc[0]
+    n = index.n_rows
+    if n <= FULL_RANKING_PAGED_MAX:
+        # exact full ranking with the fused kernel alone: ceil(N/128) rank-continuation passes (ComoRAG-scale
+        # corpora have 1e3-1e4 passages; each pass over such a shard is a few tens of microseconds)
+        ids, scores, minmax = index.search(query_embedding, max(n, 1))
+        valid = ids[0] >= 0
+        return ids[0][valid], normalize_topk_scores(scores, minmax)[0][valid]
+    # big shards: all N scores in one device pass, sorted on the device (a permutation of 1e6+ rows is not a top-k)
     q = index.prepare_queries(query_embedding)
     scores = (index.matrix().float() @ q[0, : index.dim].float())  # [N] fp32 on device
     mn, mx = scores.min(), scores.max()
