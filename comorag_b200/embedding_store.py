@@ -128,12 +128,23 @@ class EmbeddingStore:
             if not missing_ids:
                 return {}
             texts_to_encode = [nodes[h]["content"] for h in missing_ids]
-            missing_embeddings = self.embedding_model.batch_encode(texts_to_encode)
-            self._upsert(missing_ids, texts_to_encode, missing_embeddings)
+            device_rows = None
+            encode_dev = getattr(self.embedding_model, "encode_to_device", None)
+            if encode_dev is not None and self._index is not None and self._index_rows == self._n:
+                # index-build fast path: the encoder's device output goes straight into the bf16 shard (no host
+                # round trip); the host fp32 copy kept for get_embeddings()/parquet is the same rows read back.
+                device_rows = encode_dev(texts_to_encode)
+                missing_embeddings = device_rows.detach().float().cpu().numpy()
+            else:
+                missing_embeddings = self.embedding_model.batch_encode(texts_to_encode)
+            self._upsert(missing_ids, texts_to_encode, missing_embeddings, device_rows)
 
-    def _upsert(self, hash_ids, texts, embeddings):
+    def _upsert(self, hash_ids, texts, embeddings, device_rows=None):
         n0 = self._n
         self._append_host(embeddings)
+        if device_rows is not None and self._index is not None and self._index_rows == n0:
+            self._index.add(device_rows)
+            self._index_rows = self._n
         self.hash_ids.extend(hash_ids)
         self.texts.extend(texts)
         logger.info("Saving new records.")

@@ -251,3 +251,29 @@ def test_sixteen_threads_share_the_engine(dev, gold, tmp_path):
                     assert ids[0][j] == ref_ids[j]
         if coalesce:
             assert model._coalescer.stats["forwards"] - before < len(queries)      # requests really shared launches
+
+
+def test_incremental_insert_uses_device_rows(dev, gold, tmp_path):
+    """After the device index exists, insert_strings feeds it from the encoder's device output; the result equals a
+    store built in one go (same ids, same rows, same search)."""
+    from comorag_b200.config import EngineConfig
+    from comorag_b200.embedding_model import BGEEmbeddingModel
+    from comorag_b200.embedding_store import EmbeddingStore
+    cfg = EngineConfig(embedding_model_name=CKPT, embedding_batch_size=4, embedding_max_seq_len=512)
+    model = BGEEmbeddingModel(global_config=cfg, embedding_model_name=CKPT)
+    texts = gold["texts"].tolist()
+    a = EmbeddingStore(model, str(tmp_path / "a"), 4, "chunk")
+    a.insert_strings(texts[:5])
+    q = model.batch_encode(texts[6:9])
+    a.search(q, 3)                                   # builds the device shard
+    a.insert_strings(texts[3:])                      # 7 new rows through the device fast path
+    assert a.index.n_rows == len(texts) == len(a.hash_ids)
+    b = EmbeddingStore(model, str(tmp_path / "b"), 4, "chunk")
+    b.insert_strings(texts)
+    assert a.get_all_ids() == b.get_all_ids()
+    np.testing.assert_allclose(a.get_embeddings(a.hash_ids), b.get_embeddings(b.hash_ids), atol=1e-6)
+    ia, sa, _ = a.search(q, 5)
+    ib, sb, _ = b.search(q, 5)
+    np.testing.assert_allclose(sa, sb, atol=1e-5)
+    assert torch.equal(a.index.matrix().float().cpu(), b.index.matrix().float().cpu()) or \
+        float((a.index.matrix().float() - b.index.matrix().float()).abs().max()) < 1e-2
