@@ -211,15 +211,18 @@ class DenseIndex:
         return q
 
     def search(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-        """Host-buffer entry point: numpy in, numpy out (ids, scores, minmax)."""
+        """Host-buffer entry point: numpy in, numpy out (ids int64 [nq,k], scores fp32 [nq,k], minmax fp32 [nq,2])."""
         q = self.prepare_queries(queries)
-        ids, scores, minmax = self.search_device(q, k)
-        out = torch.cat([ids.to(torch.float64).view(-1), scores.to(torch.float64).view(-1),
-                         minmax.to(torch.float64).view(-1)]).cpu().numpy()
         nq = q.shape[0]
-        return (out[: nq * k].astype(np.int64).reshape(nq, k),
-                out[nq * k: 2 * nq * k].astype(np.float32).reshape(nq, k),
-                out[2 * nq * k:].astype(np.float32).reshape(nq, 2))
+        if k <= MAX_K:
+            # the kernel writes straight into one packed record, which comes back in a single device->host copy
+            rec = torch.empty(packed_record_bytes(nq, k), dtype=torch.uint8, device=self.device)
+            self.search_device(q, k, out=packed_views(rec, nq, k))
+            host = rec.cpu()
+            ids, scores, minmax = packed_views(host, nq, k)
+            return ids.numpy().copy(), scores.numpy().copy(), minmax.numpy().copy()
+        ids, scores, minmax = self.search_device(q, k)
+        return ids.cpu().numpy(), scores.cpu().numpy(), minmax.cpu().numpy()
 
 
 def merge_topk(scores: torch.Tensor, ids: torch.Tensor, minmax: Optional[torch.Tensor]):
