@@ -571,10 +571,10 @@ extern "C" int crag_search_topk_after(const void* corpus, int64_t n_rows, int di
   // k-th best score as the admission floor of the full scan.  The sample rows are rows of the shard, so at least k
   // rows reach the floor and nothing below it can rank in the top-k; the full scan then admits ~k * (n_rows /
   // sample_rows) candidates per query in total instead of treating the head of every CTA's stream as candidates.
-  // (A row-strided sample is statistically nicer but costs 2048 scattered 128-byte DRAM reads per CTA: 57 us
-  // measured against ~10 us for the contiguous block.)
-  // Measured on B200 (32 queries, 1.25M x 1024 rows): k=10 518 -> 463 us, k=100 1042 -> 651 us per pass; the pre-pass
-  // itself costs ~40 us, so it is skipped for small query-block x k products and small shards.
+  // (A row-strided sample is statistically nicer but reads 2048 scattered 128-byte pieces per CTA; measured
+  // sample-scan times: strided 57 us, contiguous 52 us, contiguous + direct first-tile path 37 us.)
+  // Measured on B200 (32 queries, 1.25M x 1024 rows): k=10 498 -> 443 us, k=100 1042 -> 651 us per search; the
+  // pre-pass itself costs ~55 us (scan + merge), so it is skipped for small query-block x k products.
   const int64_t sample_rows = int64_t(plan.grid) * kTileRows;
   const int64_t sample_stride = n_rows / sample_rows;
   // pays off when the selector work is a visible share of the pass: small shards (multi-GPU strong scaling) or big k
