@@ -321,18 +321,29 @@ __device__ __forceinline__ void select_stream(uint64_t* keys, uint64_t* thr_slot
   if (lane == 0) *thr_slot = 0ull;
   __syncwarp();
   int c = 0;
-  for (int base = 0; base < total; base += 32) {
-    const int idx = base + lane;
-    const uint64_t key = idx < total ? fetch(idx) : 0ull;
-    const uint64_t thr = *thr_slot > bound ? *thr_slot : bound;
-    const bool take = key != 0 && key >= thr;
-    const uint32_t m = __ballot_sync(0xffffffffu, take);
-    if (take) keys[KLIST + c + __popc(m & ((1u << lane) - 1u))] = key;
-    c += __popc(m);
-    __syncwarp();
-    if (c + 32 > CAP) {
-      flush_query<KLIST, CAP>(keys, c, k, thr_slot, lane);
-      c = 0;
+  constexpr int U = 4;  // batches fetched ahead: the lists sit in L2 / HBM, so 4 loads per lane are kept in flight
+  for (int base0 = 0; base0 < total; base0 += 32 * U) {
+    uint64_t pre[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base0 + u * 32 + lane;
+      pre[u] = idx < total ? fetch(idx) : 0ull;   // past-the-end batches are all zero and admit nothing
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t key = pre[u];
+      const uint64_t thr = *thr_slot > bound ? *thr_slot : bound;
+      const bool take = key != 0 && key >= thr;
+      const uint32_t m = __ballot_sync(0xffffffffu, take);
+      if (m != 0u) {
+        if (take) keys[KLIST + c + __popc(m & ((1u << lane) - 1u))] = key;
+        c += __popc(m);
+        __syncwarp();
+        if (c + 32 > CAP) {
+          flush_query<KLIST, CAP>(keys, c, k, thr_slot, lane);
+          c = 0;
+        }
+      }
     }
   }
   if (c > 0) flush_query<KLIST, CAP>(keys, c, k, thr_slot, lane);
