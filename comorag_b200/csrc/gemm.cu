@@ -155,6 +155,73 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
   }
 }
 
+// Same epilogue, but the bf16 chunk goes through a per-warp shared-memory staging tile first so that the global
+// stores are row-coalesced: thread = row produces 4 x 16 B of its own row (stored at pitch 80 B, conflict-free for
+// quarter-warps); then 4 lanes cover one row's 64 B and one warp instruction writes 8 rows x 64 contiguous bytes
+// (full 32-byte sectors) instead of 32 rows x 16 B.  `stage` is this warp's private 32 x 80 B tile.
+constexpr int kEpiStagePitch = 80;
+constexpr int kEpiStageBytes = 32 * kEpiStagePitch;
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&r)[32], int row, int row_base, int col0, int M,
+                                                      int N, const float* __restrict__ bias,
+                                                      const __nv_bfloat16* __restrict__ residual, int64_t ldr,
+                                                      __nv_bfloat16* __restrict__ out, int64_t ldo, uint8_t* stage,
+                                                      int lane) {
+  if (col0 >= N) return;  // warp-uniform
+  const bool row_ok = row < M;
+  const __nv_bfloat16* rrow = (EPI == GEMM_EPI_BIAS_RESIDUAL) ? residual + int64_t(row) * ldr + col0 : nullptr;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (col0 + v * 8 < N) {
+      float x[8];
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + v * 8 + 4));
+      x[0] = __uint_as_float(r[v * 8 + 0]) + b0.x;
+      x[1] = __uint_as_float(r[v * 8 + 1]) + b0.y;
+      x[2] = __uint_as_float(r[v * 8 + 2]) + b0.z;
+      x[3] = __uint_as_float(r[v * 8 + 3]) + b0.w;
+      x[4] = __uint_as_float(r[v * 8 + 4]) + b1.x;
+      x[5] = __uint_as_float(r[v * 8 + 5]) + b1.y;
+      x[6] = __uint_as_float(r[v * 8 + 6]) + b1.z;
+      x[7] = __uint_as_float(r[v * 8 + 7]) + b1.w;
+      if (EPI == GEMM_EPI_BIAS_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) gelu_erf2(x[j], x[j + 1]);
+      }
+      if (EPI == GEMM_EPI_BIAS_RESIDUAL) {
+        if (row_ok) {
+          const uint4 rv = *reinterpret_cast<const uint4*>(rrow + v * 8);
+          const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+            x[2 * j] += __bfloat162float(p.x);
+            x[2 * j + 1] += __bfloat162float(p.y);
+          }
+        }
+      }
+      o.x = pack_bf16x2(x[0], x[1]);
+      o.y = pack_bf16x2(x[2], x[3]);
+      o.z = pack_bf16x2(x[4], x[5]);
+      o.w = pack_bf16x2(x[6], x[7]);
+    }
+    *reinterpret_cast<uint4*>(stage + lane * kEpiStagePitch + v * 16) = o;
+  }
+  __syncwarp();
+  const int piece = lane & 3;
+  const int gcol = col0 + piece * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r2 = i * 8 + (lane >> 2);
+    const int grow = row_base + r2;
+    if (grow < M && gcol < N)
+      *reinterpret_cast<uint4*>(out + int64_t(grow) * ldo + gcol) =
+          *reinterpret_cast<const uint4*>(stage + r2 * kEpiStagePitch + piece * 16);
+  }
+  __syncwarp();  // the staging tile is reused by the next chunk
+}
+
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
@@ -315,7 +382,10 @@ struct Gemm2Layout {
   static constexpr int kABytes = 128 * kGemmBK * 2;         // this CTA's 128 rows of A
   static constexpr int kBBytes = (BN / 2) * kGemmBK * 2;    // this CTA's half of the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr size_t smem_bytes() { return 1024 + size_t(STAGES) * kStageBytes + (2 * STAGES + 4) * 8 + 16; }
+  static constexpr size_t kBarBytes = 256;  // (2*STAGES + 4) mbarriers + the TMEM slot, rounded up
+  static constexpr size_t smem_bytes(int epi_warps) {
+    return 1024 + size_t(STAGES) * kStageBytes + kBarBytes + size_t(epi_warps) * kEpiStageBytes;
+  }
 };
 
 template <int BN, int STAGES, int EPI, int EPI_WARPS>
@@ -414,13 +484,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
   } else {
     const int quad = warp & 3;
+    uint8_t* stage = smem + STAGES * L::kStageBytes + L::kBarBytes + (warp - 2) * kEpiStageBytes;
     constexpr int kColsPerWarp = BN / (EPI_WARPS / 4);
     const int col_begin = ((warp - 2) >> 2) * kColsPerWarp;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
-      const int row = m_blk * 256 + int(cta) * 128 + quad * 32 + lane;
+      const int row_base = m_blk * 256 + int(cta) * 128 + quad * 32;
+      const int row = row_base + lane;
       const int n0 = n_blk * BN + col_begin;
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
@@ -430,7 +502,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c * 32, r);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(r, row, n0 + c * 32, M, N, bias, residual, ldr, out, ldo);
+        epilogue_chunk_staged<EPI>(r, row, row_base, n0 + c * 32, M, N, bias, residual, ldr, out, ldo, stage, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -454,13 +526,13 @@ static int launch_gemm2_t(const CUtensorMap& tm_a, const CUtensorMap& tm_b, int 
                           cudaStream_t stream) {
   using L = Gemm2Layout<BN, STAGES>;
   auto kern = gemm2_bf16_kernel<BN, STAGES, EPI, EPI_WARPS>;
-  CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L::smem_bytes())));
+  CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L::smem_bytes(EPI_WARPS))));
   const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   int pairs = sms / 2;
   if (tiles < pairs) pairs = tiles;
-  kern<<<2 * pairs, 64 + 32 * EPI_WARPS, L::smem_bytes(), stream>>>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo);
+  kern<<<2 * pairs, 64 + 32 * EPI_WARPS, L::smem_bytes(EPI_WARPS), stream>>>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo);
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }
