@@ -70,6 +70,16 @@ def dense_passage_retrieval(index: DenseIndex, query_embedding, top_k: Optional[
     return order.cpu().numpy(), norm[order].cpu().numpy()
 
 
+def get_fact_scores(index: DenseIndex, query_embedding) -> np.ndarray:
+    """ComoRAG.py:937-948: min-max-normalised score of EVERY fact row, in row order (callers slice it with
+    np.argsort(...)[-k:][::-1], ComoRAG.py:475 / :1073 -- prefer get_fact_scores_topk for that).  Built from the
+    exact full ranking (rank continuation for ComoRAG-scale fact tables, device pass beyond that)."""
+    order, sorted_scores = dense_passage_retrieval(index, query_embedding)
+    out = np.empty(index.n_rows, dtype=np.float32)
+    out[order] = sorted_scores
+    return out
+
+
 def get_fact_scores_topk(index: DenseIndex, query_embedding, link_top_k: int) -> Tuple[np.ndarray, np.ndarray]:
     """get_fact_scores + the argsort[-k:][::-1] pick that follows it (ComoRAG.py:937-948, :475, :1073)."""
     ids, sc = dense_topk(index, query_embedding, link_top_k)

@@ -87,3 +87,28 @@ def test_rerank_surface_keeps_reference_contract():
     assert f.rerank("x", [], [], 3) == ([], [], {"confidence": None})
     idx_all, _, _ = f("slipper", items, [0, 1, 2])          # len_after_rerank=None keeps everything
     assert idx_all == [1, 2, 0]                              # tie between items 1 and 2 -> candidate order
+
+
+def test_full_score_contracts_on_a_fake_index():
+    """get_fact_scores / dense_passage_retrieval(top_k=None) rebuild the reference's full-array contracts from the
+    ranked output of DenseIndex.search (checked against the numpy oracle with a CPU stand-in for the index)."""
+    from comorag_b200 import retrieval as rt
+    rng = np.random.default_rng(4)
+    E = rng.standard_normal((300, 16)).astype(np.float32)
+    q = rng.standard_normal((1, 16)).astype(np.float32)
+
+    class FakeIndex:
+        n_rows = 300
+
+        def search(self, queries, k):
+            sc = np.asarray(queries, np.float32) @ E.T
+            ids = np.argsort(-sc, axis=1, kind="stable")[:, :k]
+            return ids, np.take_along_axis(sc, ids, 1), np.stack([sc.min(1), sc.max(1)], 1)
+
+    ids, scores = rt.dense_passage_retrieval(FakeIndex(), q)
+    want_ids, want_scores = so.dense_passage_retrieval(E, q)
+    np.testing.assert_array_equal(ids, want_ids)
+    np.testing.assert_allclose(scores, want_scores, atol=1e-6)
+    np.testing.assert_allclose(rt.get_fact_scores(FakeIndex(), q), so.fact_scores(E, q), atol=1e-6)
+    top_ids, top_sc = rt.get_fact_scores_topk(FakeIndex(), q, 5)
+    np.testing.assert_array_equal(top_ids, so.top_facts(so.fact_scores(E, q), 5))
