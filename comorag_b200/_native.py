@@ -37,6 +37,7 @@ SIGNATURES = {
     # struct-taking entry points get their argtypes in comorag_b200/encoder.py
     "crag_encoder_workspace_bytes": (C.c_size_t, None),
     "crag_encoder_forward": (C.c_int, None),
+    "crag_encoder_classify": (C.c_int, None),
     "crag_attention_varlen": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p]),
     "crag_attention_varlen_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

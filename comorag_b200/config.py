@@ -24,6 +24,8 @@ class EngineConfig:
     embedding_coalesce: bool = False                      # batch concurrent callers' encodes/searches (coalescer.py)
     embedding_coalesce_wait_ms: float = 0.3
     embedding_coalesce_max_texts: int = 64
+    rerank_model_name: str = ""                           # sequence-classification checkpoint dir -> cross-encoder rerank
+    rerank_max_seq_len: int = 512
 
 
 def cfg_get(cfg, name: str, default=None):

@@ -56,27 +56,24 @@ extern "C" size_t crag_encoder_workspace_bytes(const crag_encoder* model, int to
   return carve(nullptr, total_tokens, model->hidden, model->intermediate).total;
 }
 
-extern "C" int crag_encoder_forward(const crag_encoder* model, const int32_t* token_ids, const int32_t* cu_seqlens,
-                                    int n_seqs, int total_tokens, int max_seqlen, int normalize, float* out_f32,
-                                    void* out_bf16, int64_t out_bf16_stride, void* workspace,
-                                    size_t workspace_bytes, crag_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int rc = check_model(model);
-  if (rc != CRAG_OK) return rc;
-  if (n_seqs < 0 || total_tokens < 0 || max_seqlen < 0) return fail(CRAG_ERR_INVALID, "encoder: negative sizes");
-  if (n_seqs == 0) return CRAG_OK;
-  if (!token_ids || !cu_seqlens || !workspace || (!out_f32 && !out_bf16)) return fail(CRAG_ERR_INVALID, "encoder: null pointer");
+namespace crag {
+namespace {
+
+// Validates the batch, carves the workspace and runs embeddings + all layers; on success b.x holds last_hidden_state
+// (bf16 [total_tokens, H]).
+int run_layers(const crag_encoder* model, const int32_t* token_ids, const int32_t* cu_seqlens, int n_seqs,
+               int total_tokens, int max_seqlen, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+               EncoderBuffers& b) {
+  if (!token_ids || !cu_seqlens || !workspace) return fail(CRAG_ERR_INVALID, "encoder: null pointer");
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(CRAG_ERR_INVALID, "encoder: workspace must be 256-byte aligned");
-  if (out_bf16 && (out_bf16_stride < model->hidden || out_bf16_stride % 8 || (reinterpret_cast<uintptr_t>(out_bf16) & 15)))
-    return fail(CRAG_ERR_INVALID, "encoder: out_bf16 stride/alignment");
   if (max_seqlen > model->max_pos - model->pos_offset) return fail(CRAG_ERR_INVALID, "encoder: max_seqlen %d exceeds the position table (%d - %d)", max_seqlen, model->max_pos, model->pos_offset);
   const int T = total_tokens, H = model->hidden, I = model->intermediate;
-  EncoderBuffers b = carve(workspace, T, H, I);
+  b = carve(workspace, T, H, I);
   if (workspace_bytes < b.total) return fail(CRAG_ERR_WORKSPACE, "encoder: workspace %zu < %zu bytes", workspace_bytes, b.total);
 
-  rc = launch_embed_layernorm(token_ids, cu_seqlens, n_seqs, T, H, model->vocab, model->max_pos, model->pos_offset,
-                              model->word_emb, model->pos_emb, model->type_emb, model->emb_ln_g, model->emb_ln_b,
-                              model->ln_eps, b.x, stream);
+  int rc = launch_embed_layernorm(token_ids, cu_seqlens, n_seqs, T, H, model->vocab, model->max_pos, model->pos_offset,
+                                  model->word_emb, model->pos_emb, model->type_emb, model->emb_ln_g, model->emb_ln_b,
+                                  model->ln_eps, b.x, stream);
   if (rc != CRAG_OK) return rc;
   for (int l = 0; l < model->n_layers; ++l) {
     const crag_encoder_layer& w = model->layers[l];
@@ -98,7 +95,48 @@ extern "C" int crag_encoder_forward(const crag_encoder* model, const int32_t* to
     rc = launch_layernorm(b.tmp, T, H, w.ln2_g, w.ln2_b, model->ln_eps, b.x, stream);
     if (rc != CRAG_OK) return rc;
   }
-  return launch_pool_normalize(b.x, cu_seqlens, n_seqs, H, normalize, out_f32, out_bf16, out_bf16_stride, stream);
+  return CRAG_OK;
+}
+
+}  // namespace
+}  // namespace crag
+
+extern "C" int crag_encoder_forward(const crag_encoder* model, const int32_t* token_ids, const int32_t* cu_seqlens,
+                                    int n_seqs, int total_tokens, int max_seqlen, int normalize, float* out_f32,
+                                    void* out_bf16, int64_t out_bf16_stride, void* workspace,
+                                    size_t workspace_bytes, crag_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_model(model);
+  if (rc != CRAG_OK) return rc;
+  if (n_seqs < 0 || total_tokens < 0 || max_seqlen < 0) return fail(CRAG_ERR_INVALID, "encoder: negative sizes");
+  if (n_seqs == 0) return CRAG_OK;
+  if (!out_f32 && !out_bf16) return fail(CRAG_ERR_INVALID, "encoder: null pointer");
+  if (out_bf16 && (out_bf16_stride < model->hidden || out_bf16_stride % 8 || (reinterpret_cast<uintptr_t>(out_bf16) & 15)))
+    return fail(CRAG_ERR_INVALID, "encoder: out_bf16 stride/alignment");
+  EncoderBuffers b;
+  rc = run_layers(model, token_ids, cu_seqlens, n_seqs, total_tokens, max_seqlen, workspace, workspace_bytes, stream, b);
+  if (rc != CRAG_OK) return rc;
+  return launch_pool_normalize(b.x, cu_seqlens, n_seqs, model->hidden, normalize, out_f32, out_bf16, out_bf16_stride, stream);
+}
+
+// Cross-encoder scoring: the same layers, then the classification head on every sequence's first token.
+extern "C" int crag_encoder_classify(const crag_encoder* model, const crag_classifier_head* head,
+                                     const int32_t* token_ids, const int32_t* cu_seqlens, int n_seqs,
+                                     int total_tokens, int max_seqlen, float* logits, void* workspace,
+                                     size_t workspace_bytes, crag_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_model(model);
+  if (rc != CRAG_OK) return rc;
+  if (!head || !head->w_dense || !head->b_dense || !head->w_out || !head->b_out) return fail(CRAG_ERR_INVALID, "classify: null head weights");
+  if (head->n_labels < 1) return fail(CRAG_ERR_INVALID, "classify: n_labels %d", head->n_labels);
+  if (n_seqs < 0 || total_tokens < 0 || max_seqlen < 0) return fail(CRAG_ERR_INVALID, "encoder: negative sizes");
+  if (n_seqs == 0) return CRAG_OK;
+  if (!logits) return fail(CRAG_ERR_INVALID, "classify: null logits");
+  EncoderBuffers b;
+  rc = run_layers(model, token_ids, cu_seqlens, n_seqs, total_tokens, max_seqlen, workspace, workspace_bytes, stream, b);
+  if (rc != CRAG_OK) return rc;
+  return launch_cls_head(b.x, cu_seqlens, n_seqs, model->hidden, head->w_dense, head->b_dense, head->w_out, head->b_out,
+                         head->n_labels, logits, stream);
 }
 
 // Stand-alone pooling entry (K3), for callers that already hold last_hidden_state.

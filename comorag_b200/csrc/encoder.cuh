@@ -17,5 +17,8 @@ int launch_attention_tc(const void* qkv, const int32_t* cu_seqlens, int n_seqs, 
                         int heads, void* ctx, cudaStream_t stream);
 int launch_pool_normalize(const void* hidden, const int32_t* cu_seqlens, int n_seqs, int H, int normalize,
                           float* out_f32, void* out_bf16, int64_t out_bf16_stride, cudaStream_t stream);
+int launch_cls_head(const void* hidden, const int32_t* cu_seqlens, int n_seqs, int H, const void* w_dense,
+                    const float* b_dense, const void* w_out, const float* b_out, int n_labels, float* logits,
+                    cudaStream_t stream);
 
 }  // namespace crag

@@ -440,6 +440,57 @@ __global__ void __launch_bounds__(128 * kPoolGroups) pool_normalize_kernel(const
   }
 }
 
+// ------------------------------------------------- classification head
+// Sequence-classification head on the FIRST token of every sequence (the cross-encoder rerank score):
+//   logits = W_out tanh(W_dense h[<s>] + b_dense) + b_out
+// (HF XLMRobertaClassificationHead; dropout is the identity in eval).  One block per sequence, 8 warps: a warp owns
+// output features o, o+8, ... and its lanes stride the H inputs in 16-byte vectors, so every weight row is read as
+// contiguous 512-byte segments (L2-resident after the first block).  H <= 1024, multiple of 8.
+constexpr int kClsWarps = 8;
+__device__ __forceinline__ float warp_dot_bf16(const __nv_bfloat16* __restrict__ wr, const float* s_in, int nvec, int lane) {
+  float acc = 0.f;
+  for (int vec = lane; vec < nvec; vec += 32) {
+    float f[8];
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(wr + vec * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(f[j], s_in[vec * 8 + j], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+__global__ void __launch_bounds__(32 * kClsWarps) cls_head_kernel(const __nv_bfloat16* __restrict__ hidden,
+                                                                  const int32_t* __restrict__ cu_seqlens, int H,
+                                                                  const __nv_bfloat16* __restrict__ w_dense,
+                                                                  const float* __restrict__ b_dense,
+                                                                  const __nv_bfloat16* __restrict__ w_out,
+                                                                  const float* __restrict__ b_out, int n_labels,
+                                                                  float* __restrict__ logits) {
+  __shared__ float s_x[1024];
+  __shared__ float s_y[1024];
+  const int seq = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = H / 8;
+  const __nv_bfloat16* row = hidden + int64_t(__ldg(cu_seqlens + seq)) * H;
+  for (int vec = threadIdx.x; vec < nvec; vec += 32 * kClsWarps) {
+    float f[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(row + vec * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_x[vec * 8 + j] = f[j];
+  }
+  __syncthreads();
+  for (int o = warp; o < H; o += kClsWarps) {
+    const float acc = warp_dot_bf16(w_dense + int64_t(o) * H, s_x, nvec, lane);
+    if (lane == 0) s_y[o] = tanhf(acc + __ldg(b_dense + o));
+  }
+  __syncthreads();
+  for (int o = warp; o < n_labels; o += kClsWarps) {
+    const float acc = warp_dot_bf16(w_out + int64_t(o) * H, s_y, nvec, lane);
+    if (lane == 0) logits[int64_t(seq) * n_labels + o] = acc + __ldg(b_out + o);
+  }
+}
+
 // -------------------------------------------------------------- launchers
 int launch_embed_layernorm(const int32_t* token_ids, const int32_t* cu_seqlens, int n_seqs, int T, int H, int vocab,
                            int max_pos, int pos_offset, const void* word_emb, const void* pos_emb,
@@ -505,6 +556,19 @@ int launch_pool_normalize(const void* hidden, const int32_t* cu_seqlens, int n_s
   pool_normalize_kernel<<<n_seqs, 128 * kPoolGroups, smem, stream>>>(static_cast<const __nv_bfloat16*>(hidden), cu_seqlens, H,
                                                                      normalize, out_f32, static_cast<__nv_bfloat16*>(out_bf16),
                                                                      out_bf16_stride);
+  CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
+}
+
+int launch_cls_head(const void* hidden, const int32_t* cu_seqlens, int n_seqs, int H, const void* w_dense,
+                    const float* b_dense, const void* w_out, const float* b_out, int n_labels, float* logits,
+                    cudaStream_t stream) {
+  if (n_seqs <= 0) return CRAG_OK;
+  if (H > 1024 || H % 8) return fail(CRAG_ERR_UNSUPPORTED, "classifier head: hidden size %d unsupported (<= 1024, multiple of 8)", H);
+  if (n_labels < 1) return fail(CRAG_ERR_INVALID, "classifier head: n_labels %d", n_labels);
+  cls_head_kernel<<<n_seqs, 32 * kClsWarps, 0, stream>>>(static_cast<const __nv_bfloat16*>(hidden), cu_seqlens, H,
+                                                         static_cast<const __nv_bfloat16*>(w_dense), b_dense,
+                                                         static_cast<const __nv_bfloat16*>(w_out), b_out, n_labels, logits);
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }

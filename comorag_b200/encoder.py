@@ -79,6 +79,11 @@ class _Model(C.Structure):
                 ("emb_ln_g", C.c_void_p), ("emb_ln_b", C.c_void_p), ("layers", C.POINTER(_Layer))]
 
 
+class _Head(C.Structure):
+    _fields_ = [("w_dense", C.c_void_p), ("b_dense", C.c_void_p), ("w_out", C.c_void_p), ("b_out", C.c_void_p),
+                ("n_labels", C.c_int32)]
+
+
 def _bind_encoder_abi(lib) -> None:
     if getattr(lib, "_crag_encoder_bound", False):
         return
@@ -87,6 +92,9 @@ def _bind_encoder_abi(lib) -> None:
     lib.crag_encoder_forward.restype = C.c_int
     lib.crag_encoder_forward.argtypes = [C.POINTER(_Model), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.crag_encoder_classify.restype = C.c_int
+    lib.crag_encoder_classify.argtypes = [C.POINTER(_Model), C.POINTER(_Head), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib._crag_encoder_bound = True
 
 
@@ -114,6 +122,17 @@ class BertEncoderB200:
 
     def _build(self, sd: Dict[str, torch.Tensor]) -> None:
         cfg = self.config
+        # sequence-classification checkpoints (bge-reranker-*): head weights sit beside the prefixed encoder
+        self._head = None
+        self.n_labels = 0
+        if "classifier.dense.weight" in sd and "classifier.out_proj.weight" in sd:
+            h = _Head()
+            h.w_dense = self._dev(sd["classifier.dense.weight"], torch.bfloat16).data_ptr()
+            h.b_dense = self._dev(sd["classifier.dense.bias"], torch.float32).data_ptr()
+            h.w_out = self._dev(sd["classifier.out_proj.weight"], torch.bfloat16).data_ptr()
+            h.b_out = self._dev(sd["classifier.out_proj.bias"], torch.float32).data_ptr()
+            h.n_labels = self.n_labels = int(sd["classifier.out_proj.weight"].shape[0])
+            self._head = h
         # accept both "bert."/"roberta."-prefixed and bare BertModel keys
         for pref in ("bert.", "roberta.", "model."):
             if any(k.startswith(pref + "embeddings.") for k in sd):
@@ -209,6 +228,51 @@ class BertEncoderB200:
         cu = cu.pin_memory()
         return self.forward_packed(flat.to(self.device, non_blocking=True), cu.to(self.device, non_blocking=True),
                                    max(lens), normalize)
+
+    # ------------------------------------------------- cross-encoder scoring
+    def classify_packed(self, token_ids: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int,
+                        stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """Packed pair sequences -> classification-head logits fp32 [n, n_labels] (device).  Needs a checkpoint with
+        `classifier.*` weights (XLMRobertaForSequenceClassification layout, e.g. bge-reranker-large)."""
+        if self._head is None:
+            raise _native.NativeError("this checkpoint has no classifier head (classifier.dense / classifier.out_proj)")
+        n, T, dev = cu_seqlens.numel() - 1, token_ids.numel(), self.device
+        with torch.cuda.device(dev):
+            st = stream if stream is not None else torch.cuda.current_stream(dev)
+            with torch.cuda.stream(st):
+                logits = torch.empty((n, self.n_labels), dtype=torch.float32, device=dev)
+                ws_bytes = self.workspace_bytes(T)
+                ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=dev)
+                rc = self._lib.crag_encoder_classify(C.byref(self._model), C.byref(self._head), token_ids.data_ptr(),
+                                                     cu_seqlens.data_ptr(), n, T, int(max_seqlen), logits.data_ptr(),
+                                                     ws.data_ptr(), ws_bytes, st.cuda_stream)
+                _native.check(rc, "crag_encoder_classify")
+        return logits
+
+    def classify_token_lists(self, seqs: Sequence[Sequence[int]]) -> torch.Tensor:
+        if len(seqs) == 0:
+            return torch.empty((0, self.n_labels), dtype=torch.float32, device=self.device)
+        flat, cu, longest = _pack(seqs, self.device)
+        return self.classify_packed(flat, cu, longest)
+
+
+def _pack(seqs: Sequence[Sequence[int]], device: torch.device):
+    lens = [len(s) for s in seqs]
+    if min(lens) < 1:
+        raise ValueError("empty token sequence")
+    flat = torch.tensor([t for s in seqs for t in s], dtype=torch.int32).pin_memory()
+    cu = torch.zeros(len(seqs) + 1, dtype=torch.int32)
+    cu[1:] = torch.tensor(lens, dtype=torch.int32).cumsum(0)
+    return flat.to(device, non_blocking=True), cu.pin_memory().to(device, non_blocking=True), max(lens)
+
+
+def random_head_state_dict(cfg: EncoderConfig, n_labels: int = 1, seed: int = 0, std: float = 0.02, device="cpu"):
+    """XLMRobertaClassificationHead-shaped random weights (classifier.dense / classifier.out_proj)."""
+    g = torch.Generator(device=device).manual_seed(seed + 7919)
+    H = cfg.hidden_size
+    w = lambda *shape: torch.randn(*shape, generator=g, device=device, dtype=torch.float32) * std
+    return {"classifier.dense.weight": w(H, H), "classifier.dense.bias": w(H),
+            "classifier.out_proj.weight": w(n_labels, H), "classifier.out_proj.bias": w(n_labels)}
 
 
 def random_state_dict(cfg: EncoderConfig, seed: int = 0, std: float = 0.02, device="cpu") -> Dict[str, torch.Tensor]:

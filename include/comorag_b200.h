@@ -209,6 +209,25 @@ CRAG_API int crag_encoder_forward(const crag_encoder* model, const int32_t* toke
                                   void* out_bf16, int64_t out_bf16_stride, void* workspace, size_t workspace_bytes,
                                   crag_stream_t stream);
 
+/* Cross-encoder rerank score (BASELINE config 5: bge-reranker-large behind the DSPyFilter call surface,
+ * rerank.py:97-123 -- the reference's filter is an LLM prompt, so the arithmetic here follows the published
+ * XLMRobertaForSequenceClassification forward instead: encoder layers, then on each sequence's FIRST token
+ * logits = out_proj(tanh(dense(h))) ).  Weights: device bf16 [out, in]; biases device fp32. */
+typedef struct crag_classifier_head {
+  const void* w_dense;   /* [H, H]: classifier.dense.weight */
+  const float* b_dense;  /* [H] */
+  const void* w_out;     /* [n_labels, H]: classifier.out_proj.weight */
+  const float* b_out;    /* [n_labels] */
+  int32_t n_labels;      /* 1 for bge-reranker-* */
+} crag_classifier_head;
+
+/* Packed (query, passage) token sequences -> logits fp32 [n_seqs, n_labels] on the device.  Batch arguments and
+ * workspace as crag_encoder_forward. */
+CRAG_API int crag_encoder_classify(const crag_encoder* model, const crag_classifier_head* head,
+                                   const int32_t* token_ids, const int32_t* cu_seqlens, int n_seqs, int total_tokens,
+                                   int max_seqlen, float* logits, void* workspace, size_t workspace_bytes,
+                                   crag_stream_t stream);
+
 /* K3 on its own: masked mean pool + optional L2 normalise of a packed
  * last_hidden_state (bf16 [total_tokens, hidden_size]); mean_pooling
  * (BGEEmbedding.py:15-28) + F.normalize (:127). */

@@ -81,3 +81,26 @@ def encode_token_lists(sd: Dict[str, torch.Tensor], cfg, seqs: Sequence[Sequence
                 e = F.normalize(e, p=2, dim=1)
             outs.append(e)
     return torch.cat(outs, 0) if outs else torch.empty((0, cfg.hidden_size), device=dev)
+
+
+def classifier_logits(sd: Dict[str, torch.Tensor], head: Dict[str, torch.Tensor], cfg, seqs: Sequence[Sequence[int]],
+                      batch_size: int = 32, pad_id: int = 1) -> torch.Tensor:
+    """Cross-encoder score of packed (query, passage) sequences: HF XLMRobertaForSequenceClassification's published
+    forward -- encoder, then XLMRobertaClassificationHead on the first token (<s>): out_proj(tanh(dense(h[:, 0]))).
+    The reference has no such arithmetic (rerank.py:97-123 is an LLM prompt), so this is pinned
+    against the `transformers` implementation itself (tests/test_oracle_encoder.py), not against the reference."""
+    dev = next(iter(sd.values())).device
+    outs: List[torch.Tensor] = []
+    with torch.no_grad():
+        for s0 in range(0, len(seqs), batch_size):
+            chunk = seqs[s0:s0 + batch_size]
+            L = max(len(s) for s in chunk)
+            ids = torch.full((len(chunk), L), pad_id, dtype=torch.long, device=dev)
+            mask = torch.zeros((len(chunk), L), dtype=torch.long, device=dev)
+            for i, s in enumerate(chunk):
+                ids[i, :len(s)] = torch.tensor(list(s), dtype=torch.long, device=dev)
+                mask[i, :len(s)] = 1
+            h0 = bert_forward(sd, cfg, ids, mask)[:, 0]
+            y = torch.tanh(F.linear(h0, head["classifier.dense.weight"].float(), head["classifier.dense.bias"].float()))
+            outs.append(F.linear(y, head["classifier.out_proj.weight"].float(), head["classifier.out_proj.bias"].float()))
+    return torch.cat(outs, 0)

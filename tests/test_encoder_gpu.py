@@ -277,3 +277,35 @@ def test_incremental_insert_uses_device_rows(dev, gold, tmp_path):
     np.testing.assert_allclose(sa, sb, atol=1e-5)
     assert torch.equal(a.index.matrix().float().cpu(), b.index.matrix().float().cpu()) or \
         float((a.index.matrix().float() - b.index.matrix().float()).abs().max()) < 1e-2
+
+
+@pytest.mark.parametrize("cargs,lens,std,tol", [((128, 2, 2, 256, 1000), [4, 100, 257, 510], 0.06, 3e-2),
+                                                ((1024, 24, 16, 4096, 3000), [512, 77], 0.02, 6e-2)])
+def test_cross_encoder_logits_match_oracle(dev, cargs, lens, std, tol):
+    """bge-reranker-* architecture (XLM-R encoder + classification head on <s>): crag_encoder_classify against the
+    fp32 oracle on the same bf16-rounded weights; the large case is bge-reranker-large's shape (BASELINE config 5)
+    with a cut-down vocabulary.  Pre-tanh activations are O(1) (head std 0.1 at H=128, scaled 1/sqrt(H)); absolute
+    tolerance 3e-2 (2 layers) / 6e-2 (24 layers of bf16 activations feeding a 1024-term dot)."""
+    from comorag_b200.encoder import BertEncoderB200, EncoderConfig, random_head_state_dict, random_state_dict
+    cfg = EncoderConfig(*cargs, max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5, position_offset=2)
+    sd = random_state_dict(cfg, seed=9, std=std, device=dev)
+    head = random_head_state_dict(cfg, n_labels=1, seed=9, std=0.1 * (128 / cfg.hidden_size) ** 0.5, device=dev)
+    enc = BertEncoderB200(cfg, {**{"roberta." + k: v for k, v in sd.items()}, **head}, dev)
+    assert enc.n_labels == 1
+    g = torch.Generator().manual_seed(4)
+    seqs = [[0] + torch.randint(5, cfg.vocab_size, (n - 2,), generator=g).tolist() + [2] for n in lens]
+    got = enc.classify_token_lists(seqs)
+    q = lambda d: {k: (v.bfloat16().float() if v.dim() == 2 else v) for k, v in d.items()}
+    want = eo.classifier_logits(q(sd), q(head), cfg, seqs, pad_id=1)
+    assert got.shape == want.shape == (len(lens), 1)
+    assert float(want.abs().max()) > 0.05                         # the comparison is not vacuous
+    assert float((got - want).abs().max()) < tol
+    # pooled embeddings of the same checkpoint are untouched by the head
+    emb = enc.encode_token_lists(seqs[:2])
+    ref = eo.encode_token_lists(q(sd), cfg, seqs[:2], pad_id=1)
+    assert float(torch.nn.functional.cosine_similarity(emb, ref, dim=1).min()) > 0.999
+    # a checkpoint without classifier weights refuses instead of scoring with garbage
+    plain = BertEncoderB200(cfg, sd, dev) if cfg.hidden_size == 128 else None
+    if plain is not None:
+        with pytest.raises(Exception):
+            plain.classify_token_lists(seqs[:1])

@@ -112,3 +112,51 @@ def test_full_score_contracts_on_a_fake_index():
     np.testing.assert_allclose(rt.get_fact_scores(FakeIndex(), q), so.fact_scores(E, q), atol=1e-6)
     top_ids, top_sc = rt.get_fact_scores_topk(FakeIndex(), q, 5)
     np.testing.assert_array_equal(top_ids, so.top_facts(so.fact_scores(E, q), 5))
+
+
+def test_cross_encoder_reranker_host_logic():
+    """Pair tokenisation, budget-cut launches over length-sorted pairs, un-permutation and the DSPyFilter return
+    convention -- with a CPU stand-in for the device encoder (the arithmetic is covered by the -m gpu tests)."""
+    import os
+    import torch
+    from transformers import AutoTokenizer
+    from comorag_b200.rerank import CrossEncoderReranker, DSPyFilter
+    tok = AutoTokenizer.from_pretrained(os.path.join(os.path.dirname(__file__), "golden", "bge-tiny-synth"))
+
+    class FakeEncoder:
+        n_labels = 1
+        launches = []
+
+        class config:
+            max_position_embeddings, position_offset = 64, 0
+
+        def classify_token_lists(self, seqs):
+            self.launches.append([len(s) for s in seqs])
+            return torch.tensor([[float(sum(s) % 97) + 0.001 * len(s)] for s in seqs])
+
+    enc = FakeEncoder()
+    rr = CrossEncoderReranker("unused", encoder=enc, tokenizer=tok, max_length=512, token_budget=40)
+    assert rr.max_length == 64                                   # clamped to the position table
+    pairs = [("who lost a slipper", "cinderella lost her glass slipper at the ball " * (i % 4 + 1)) for i in range(9)]
+    ids = tok([q for q, _ in pairs], [p for _, p in pairs], truncation=True, max_length=64)["input_ids"]
+    want = np.array([float(sum(s) % 97) + 0.001 * len(s) for s in ids], dtype=np.float32)
+    got = rr.score(pairs)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+    assert len(enc.launches) > 1 and all(sum(l) <= 40 or len(l) == 1 for l in enc.launches)
+    assert all(max(l) <= 64 for l in enc.launches)
+    assert rr.score([]).shape == (0,)
+    order, sc = rr.rerank_passages("who lost a slipper", [p for _, p in pairs], top_k=3)
+    assert list(order) == list(np.argsort(-want.astype(np.float64), kind="stable")[:3])
+
+    class Host:
+        global_config = type("Cfg", (), {})()
+        embedding_model = None
+
+    flt = DSPyFilter(Host())
+    flt.cross_encoder = rr
+    items = [("cinderella", "lost", "slipper"), ("prince", "found", "slipper"), ("fairy", "made", "coach")]
+    idx, kept, meta = flt("who lost a slipper", items, [7, 8, 9], 2)
+    s = rr.score([("who lost a slipper", " ".join(t)) for t in items])
+    o = np.argsort(-s.astype(np.float64), kind="stable")[:2]
+    assert idx == [[7, 8, 9][i] for i in o] and kept == [items[i] for i in o] and len(meta["confidence"]) == 2
+    assert flt("q", [], [], 5) == ([], [], {"confidence": None})

@@ -75,3 +75,29 @@ def test_oracle_matches_hf_xlm_roberta_positions():
         out = hf(input_ids=ids, attention_mask=mask).last_hidden_state
     want = torch.nn.functional.normalize(eo.mean_pooling(out, mask), dim=1)
     assert float((got - want).abs().max()) < 2e-6
+
+
+def test_classifier_oracle_matches_hf_sequence_classification():
+    """The cross-encoder oracle (encoder + head on <s>) equals HF's XLMRobertaForSequenceClassification (the
+    bge-reranker-* architecture) on a random small checkpoint, padded batch included."""
+    from transformers import XLMRobertaConfig, XLMRobertaForSequenceClassification
+    hf_cfg = XLMRobertaConfig(vocab_size=300, hidden_size=64, num_hidden_layers=2, num_attention_heads=2, intermediate_size=128,
+                              max_position_embeddings=130, type_vocab_size=1, pad_token_id=1, layer_norm_eps=1e-5, num_labels=1)
+    torch.manual_seed(11)
+    hf = XLMRobertaForSequenceClassification(hf_cfg).eval()
+    full = hf.state_dict()
+    sd = {k[len("roberta."):]: v for k, v in full.items() if k.startswith("roberta.")}
+    head = {k: v for k, v in full.items() if k.startswith("classifier.")}
+    cfg = EncoderConfig(64, 2, 2, 128, 300, max_position_embeddings=130, type_vocab_size=1, layer_norm_eps=1e-5, position_offset=2)
+    seqs = [[0, 17, 45, 2, 2, 99, 120, 2], [0] + list(range(10, 40)) + [2, 2] + list(range(50, 90)) + [2]]
+    got = eo.classifier_logits(sd, head, cfg, seqs, pad_id=1)
+    L = max(len(s) for s in seqs)
+    ids = torch.full((2, L), 1, dtype=torch.long)
+    mask = torch.zeros((2, L), dtype=torch.long)
+    for i, s_ in enumerate(seqs):
+        ids[i, :len(s_)] = torch.tensor(s_)
+        mask[i, :len(s_)] = 1
+    with torch.no_grad():
+        want = hf(input_ids=ids, attention_mask=mask).logits
+    assert got.shape == want.shape == (2, 1)
+    assert float((got - want).abs().max()) < 2e-6
