@@ -169,8 +169,13 @@ class EmbeddingStore:
         padded[:, : self._dim] = torch.from_numpy(np.ascontiguousarray(rows)).to(torch.bfloat16)
         with open(self._base + ".bf16", "ab") as f:
             f.write(padded.view(torch.int16).numpy().tobytes())
-        with open(self._base + ".meta.json", "w") as f:
-            json.dump({"dim": self._dim, "dim_pad": dim_pad, "rows": self._n, "format": "comorag_b200.raw.v1"}, f)
+        # the meta file is the commit record: written last, atomically; a crash before it leaves longer data files,
+        # which _load_raw() cuts back to what the meta file vouches for
+        tmp = self._base + ".meta.json.tmp"
+        with open(tmp, "w") as f:
+            json.dump({"dim": self._dim, "dim_pad": dim_pad, "rows": self._n, "format": "comorag_b200.raw.v1",
+                       "jsonl_bytes": os.path.getsize(self._base + ".rows.jsonl")}, f)
+        os.replace(tmp, self._base + ".meta.json")
 
     def _rebuild_maps_incremental(self, n0: int) -> None:
         for i in range(n0, self._n):
@@ -186,10 +191,22 @@ class EmbeddingStore:
         if not os.path.exists(meta_p):
             return False
         meta = json.load(open(meta_p))
-        rows = [json.loads(l) for l in open(self._base + ".rows.jsonl") if l.strip()]
         n, d = meta["rows"], meta["dim"]
-        if len(rows) < n or os.path.getsize(self._base + ".f32") < n * d * 4:
-            raise ValueError(f"{self._base}: raw shard files are shorter than the {n} rows the meta file records")
+        # roll back an append that was interrupted before its meta commit
+        want = {".f32": n * d * 4, ".bf16": n * meta.get("dim_pad", (d + 63) // 64 * 64) * 2}
+        if "jsonl_bytes" in meta:
+            want[".rows.jsonl"] = meta["jsonl_bytes"]
+        for ext, size in want.items():
+            have = os.path.getsize(self._base + ext) if os.path.exists(self._base + ext) else -1
+            if have < size:
+                raise ValueError(f"{self._base}{ext}: {have} bytes, shorter than the {size} the meta file records for {n} rows")
+            if have > size:
+                logger.warning(f"{self._base}{ext}: dropping {have - size} bytes of an uncommitted append")
+                with open(self._base + ext, "r+b") as f:
+                    f.truncate(size)
+        rows = [json.loads(l) for l in open(self._base + ".rows.jsonl") if l.strip()]
+        if len(rows) < n:
+            raise ValueError(f"{self._base}.rows.jsonl: {len(rows)} rows, the meta file records {n}")
         self.hash_ids = [r["hash_id"] for r in rows[:n]]
         self.texts = [r["content"] for r in rows[:n]]
         self._dim = d
@@ -242,20 +259,28 @@ class EmbeddingStore:
             self.hash_ids, self.texts = [], []
             self._rebuild_maps()  # the reference leaves hash_id_to_text / text_to_hash_id undefined here (:106-107)
 
+    _PARQUET_MAX_VALUES = (1 << 31) - 1024   # list<float> carries int32 offsets: keep each written batch below 2^31 floats
+
     def _save_data(self):
-        """embedding_store.py:109-120: whole-file rewrite, same schema (large_string, large_string, list<float>)."""
+        """embedding_store.py:109-120: whole-file rewrite, same schema (large_string, large_string, list<float>).
+        Written in row batches so stores past 2^31 floats (2.1M rows x 1024) do not overflow the list offsets."""
         import pyarrow as pa
         import pyarrow.parquet as pq
         n, d = self._n, (self._dim or 0)
-        values = pa.array(self._host[:n].reshape(-1), type=pa.float32())
-        offsets = pa.array(np.arange(0, (n + 1) * d, d, dtype=np.int32) if d else np.zeros(n + 1, np.int32), type=pa.int32())
-        table = pa.table({
-            "hash_id": pa.array(self.hash_ids, type=pa.large_string()),
-            "content": pa.array(self.texts, type=pa.large_string()),
-            "embedding": pa.ListArray.from_arrays(offsets, values),
-        })
+        schema = pa.schema([("hash_id", pa.large_string()), ("content", pa.large_string()),
+                            ("embedding", pa.list_(pa.float32()))])
+        step = max(1, self._PARQUET_MAX_VALUES // max(d, 1))
         tmp = self.filename + ".tmp"
-        pq.write_table(table, tmp)
+        with pq.ParquetWriter(tmp, schema) as writer:
+            for s0 in range(0, max(n, 1), step):
+                s1 = min(n, s0 + step)
+                values = pa.array(self._host[s0:s1].reshape(-1), type=pa.float32())
+                offsets = pa.array(np.arange(s1 - s0 + 1, dtype=np.int64) * d, type=pa.int32())
+                writer.write_table(pa.table({
+                    "hash_id": pa.array(self.hash_ids[s0:s1], type=pa.large_string()),
+                    "content": pa.array(self.texts[s0:s1], type=pa.large_string()),
+                    "embedding": pa.ListArray.from_arrays(offsets, values),
+                }, schema=schema))
         os.replace(tmp, self.filename)
         self._rebuild_maps()
         logger.info(f"Saved {len(self.hash_ids)} records to {self.filename}")

@@ -70,6 +70,14 @@ class DenseIndex:
         """bf16 view [n_rows, dim] of the stored rows."""
         return self._buf[: self._n, : self.dim]
 
+    def _snapshot(self) -> Tuple[torch.Tensor, int]:
+        """(buffer, row count) as one consistent pair: add() may swap the buffer for a larger one while another
+        thread searches (ComoRAG.py:436-441 runs 16 threads), and reading the two fields separately could pair the
+        old pointer with the new count.  The caller's reference keeps the storage from being recycled before its
+        launch is enqueued (torch's caching allocator then orders any reuse after it on the same stream)."""
+        with self._lock:
+            return self._buf, self._n
+
     def _reserve(self, n: int) -> None:
         if n <= self._buf.shape[0]:
             return
@@ -143,6 +151,7 @@ class DenseIndex:
         nq = queries.shape[0]
         lib = _native.load()
         dev = self.device
+        buf, n_rows = self._snapshot()
         with torch.cuda.device(dev):
             st = stream if stream is not None else torch.cuda.current_stream(dev)
             with torch.cuda.stream(st):
@@ -155,8 +164,8 @@ class DenseIndex:
                 ws_bytes = lib.crag_search_workspace_bytes(nq, k)
                 ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
                 rc = lib.crag_search_topk(
-                    self._buf.data_ptr() if self._n else 0, self._n, self.dim_pad,
-                    self._buf.stride(0) if self._buf.shape[0] else self.dim_pad,
+                    buf.data_ptr() if n_rows else 0, n_rows, self.dim_pad,
+                    buf.stride(0) if buf.shape[0] else self.dim_pad,
                     self.row_offset, queries.data_ptr(), nq, k, ids.data_ptr(), scores.data_ptr(),
                     minmax.data_ptr(), ws.data_ptr(), ws_bytes, st.cuda_stream)
                 _native.check(rc, "crag_search_topk")
@@ -170,6 +179,7 @@ class DenseIndex:
         nq = queries.shape[0]
         lib = _native.load()
         dev = self.device
+        buf, n_rows = self._snapshot()
         with torch.cuda.device(dev):
             st = stream if stream is not None else torch.cuda.current_stream(dev)
             with torch.cuda.stream(st):
@@ -185,8 +195,8 @@ class DenseIndex:
                     p_sc = torch.empty((nq, kk), dtype=torch.float32, device=dev)
                     last = torch.empty((nq,), dtype=torch.int64, device=dev)   # opaque u64 positions
                     rc = lib.crag_search_topk_after(
-                        self._buf.data_ptr() if self._n else 0, self._n, self.dim_pad,
-                        self._buf.stride(0) if self._buf.shape[0] else self.dim_pad, self.row_offset,
+                        buf.data_ptr() if n_rows else 0, n_rows, self.dim_pad,
+                        buf.stride(0) if buf.shape[0] else self.dim_pad, self.row_offset,
                         queries.data_ptr(), nq, kk, _native.ptr(after), p_ids.data_ptr(), p_sc.data_ptr(),
                         minmax.data_ptr(), last.data_ptr(), ws.data_ptr(), ws_bytes, st.cuda_stream)
                     _native.check(rc, "crag_search_topk_after")

@@ -116,3 +116,48 @@ def test_append_only_persistence_roundtrip(gold, tmp_path):
     assert {n: str(schema.field(n).type) for n in schema.names} == gold["parquet_schema"]
     ref_style = EmbeddingStore(ReplayModel(gold), d, 4, "chunk")       # a parquet-mode store reads the export
     assert ref_style.get_all_ids() == gold["hash_ids"]
+
+
+def test_interrupted_append_is_rolled_back(gold, tmp_path):
+    """A crash between the data appends and the meta commit must not shift later rows: reload cuts the files back
+    to what the meta file vouches for, and the next insert lands on the right offsets."""
+    import types
+    model = ReplayModel(gold)
+    model.global_config = types.SimpleNamespace(embedding_store_append_only=True)
+    d = str(tmp_path / "chunk_embeddings")
+    store = EmbeddingStore(model, d, 4, "chunk")
+    store.insert_strings(gold["texts"][:4])
+    base = os.path.join(d, "vdb_chunk")
+    with open(base + ".f32", "ab") as f:                 # half a row of an append that never committed
+        f.write(b"\x01" * 100)
+    with open(base + ".bf16", "ab") as f:
+        f.write(b"\x02" * 300)
+    with open(base + ".rows.jsonl", "a") as f:
+        f.write('{"hash_id": "chunk-torn", "content": "torn')
+    again = EmbeddingStore(model, d, 4, "chunk")
+    assert again.get_all_ids() == gold["hash_ids"][:4]
+    again.insert_strings(gold["texts"][4:])
+    third = EmbeddingStore(model, d, 4, "chunk")
+    assert third.get_all_ids() == gold["hash_ids"] and third.texts == gold["texts"]
+    np.testing.assert_array_equal(third.get_embeddings(third.hash_ids), gold["embeddings"])
+    assert third.raw_shard_path() is not None
+    os.truncate(base + ".f32", 10)                        # data shorter than the commit record: refuse, do not guess
+    with pytest.raises(ValueError):
+        EmbeddingStore(model, d, 4, "chunk")
+
+
+def test_parquet_is_written_in_row_batches(gold, tmp_path, monkeypatch):
+    """Stores past 2^31 floats cannot be one list<float> array (int32 offsets); the writer batches rows.  Forced
+    here with a tiny batch bound: same schema, same rows after reload."""
+    monkeypatch.setattr(EmbeddingStore, "_PARQUET_MAX_VALUES", 2 * gold["embeddings"].shape[1] + 5)
+    model = ReplayModel(gold)
+    store = EmbeddingStore(model, str(tmp_path / "e"), 4, "chunk")
+    store.insert_strings(gold["texts"])
+    import pyarrow.parquet as pq
+    f = pq.ParquetFile(store.filename)
+    assert f.metadata.num_row_groups == 4 and f.metadata.num_rows == 7          # 2 + 2 + 2 + 1 rows
+    schema = pq.read_schema(store.filename)
+    assert {n: str(schema.field(n).type) for n in schema.names} == gold["parquet_schema"]
+    again = EmbeddingStore(model, str(tmp_path / "e"), 4, "chunk")
+    assert again.get_all_ids() == gold["hash_ids"]
+    np.testing.assert_array_equal(again.get_embeddings(again.hash_ids), gold["embeddings"])
