@@ -67,10 +67,18 @@ int sm_count() {
   // cached per device; a handful of devices at most
   static int cached[64] = {0};
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) {
+    fail(CRAG_ERR_CUDA, "no usable CUDA device (%s)", e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+    return -1;
+  }
   if (cached[dev] == 0) {
     int n = 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) {
+      fail(CRAG_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+      return -1;
+    }
     cached[dev] = n;
   }
   return cached[dev];
