@@ -85,3 +85,36 @@ class ShardedIndex:
         gathered = torch.empty(self.world * per, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(gathered, mine, group=self.group)
         return merge_topk_packed(gathered, self.world, nq, k)
+
+
+def pair_bounds(n_pairs: int, world: int) -> List[int]:
+    """Rank r reranks pairs [b[r], b[r+1]): contiguous, near-equal (same rule as shard_bounds)."""
+    return shard_bounds(n_pairs, world)
+
+
+def sharded_rerank(score_fn, token_lists, group: Optional[dist.ProcessGroup] = None, device=None) -> torch.Tensor:
+    """BASELINE config 5 across the GPUs of one box: after the row-sharded search every rank holds the SAME global
+    candidate list, so the (query, passage) pairs are split by rank (no data-path collective for the scoring),
+    each rank runs its slice through `score_fn(list of token lists) -> float32 [m, n_labels]` (the cross-encoder,
+    CrossEncoderReranker.score_token_lists) and ONE all-gather of the logits gives every rank all of them.
+
+    Returns float32 [n_pairs, n_labels] on `device` (default: where the local logits live), pair order preserved."""
+    n = len(token_lists)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    b = pair_bounds(n, world)
+    mine = torch.as_tensor(score_fn(token_lists[b[rank]:b[rank + 1]]), dtype=torch.float32)
+    if mine.dim() == 1:
+        mine = mine[:, None]
+    if device is not None:
+        mine = mine.to(device)
+    if world == 1:
+        return mine
+    labels = mine.shape[1]
+    per = b[1] - b[0]                      # the largest slice (the first n % world ranks hold one more pair)
+    send = torch.zeros((per, labels), dtype=torch.float32, device=mine.device)
+    send[: mine.shape[0]] = mine
+    gathered = torch.empty((world * per, labels), dtype=torch.float32, device=mine.device)
+    dist.all_gather_into_tensor(gathered, send, group=group)
+    parts = [gathered[r * per: r * per + (b[r + 1] - b[r])] for r in range(world)]
+    return torch.cat(parts, 0)

@@ -53,3 +53,35 @@ def test_two_rank_shard_merge_equals_global_topk(tmp_path, n, k):
         got = np.load(tmp_path / f"r{r}.npz")
         so.assert_topk_matches(got["ids"], got["scores"].astype(np.float64), want_i, want_s, gaps, score_tol=1e-6)
         np.testing.assert_allclose(got["mm"], want_mm, atol=1e-6)
+
+
+def _rerank_worker(rank, world, port, n_pairs, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from comorag_b200.dist import sharded_rerank
+    pairs = [[0] + list(range(5, 5 + (i % 7) + 1)) + [2] for i in range(n_pairs)]
+    seen = []
+
+    def score(token_lists):                      # stand-in for CrossEncoderReranker.score_token_lists
+        seen.append(len(token_lists))
+        return np.array([[float(sum(t)) + 0.5 * len(t)] for t in token_lists], dtype=np.float32).reshape(-1, 1)
+
+    got = sharded_rerank(score, pairs)
+    np.savez(os.path.join(out_dir, f"rr{rank}.npz"), logits=got.numpy(), seen=np.array(seen))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_pairs", [7, 8, 1])
+def test_two_rank_pair_sharded_rerank(tmp_path, n_pairs):
+    """Config 5's rerank across ranks: each rank scores only its slice of the pairs; one all-gather later every
+    rank holds every logit in pair order (ragged last slice and a rank with nothing to score included)."""
+    world = 2
+    mp.spawn(_rerank_worker, args=(world, _free_port(), n_pairs, str(tmp_path)), nprocs=world, join=True)
+    pairs = [[0] + list(range(5, 5 + (i % 7) + 1)) + [2] for i in range(n_pairs)]
+    want = np.array([[float(sum(t)) + 0.5 * len(t)] for t in pairs], dtype=np.float32)
+    sizes = []
+    for r in range(world):
+        got = np.load(tmp_path / f"rr{r}.npz")
+        np.testing.assert_array_equal(got["logits"], want)
+        sizes.append(int(got["seen"][0]))
+    assert sum(sizes) == n_pairs and max(sizes) - min(sizes) <= 1

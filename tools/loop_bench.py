@@ -1,4 +1,7 @@
-"""BASELINE config 5 on ONE GPU: the probe -> retrieve -> rerank cycle of ComoRAG's iterative loop.
+"""BASELINE config 5: the probe -> retrieve -> rerank cycle of ComoRAG's iterative loop, on one GPU
+(`python tools/loop_bench.py`) or on N GPUs of one box (`python -m torch.distributed.run --nproc-per-node N
+--master-addr 127.0.0.1 tools/loop_bench.py`: the index is row-sharded with one all-gather per search, every rank
+encodes the same probes, the rerank pairs are split by rank with one all-gather of the logits).
 
 Per cycle (ComoRAG.py:456-554 `tri_retrieve` is called once per probe; here the 32 probes of a cycle arrive as one
 wave):
@@ -37,12 +40,20 @@ def main():
     import torch
     from bench import make_shard
     from comorag_b200.encoder import BertEncoderB200, EncoderConfig, random_head_state_dict, random_state_dict
+    import torch.distributed as dist
+    from comorag_b200.dist import ShardedIndex, shard_bounds, sharded_rerank
     from comorag_b200.index import DenseIndex
     from comorag_b200.rerank import CrossEncoderReranker
 
-    dev = torch.device("cuda", 0)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    index = DenseIndex.from_tensor(make_shard(args.rows, args.dim, 1234, dev))
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    offs = shard_bounds(args.rows, world)
+    index = ShardedIndex(DenseIndex.from_tensor(make_shard(offs[rank + 1] - offs[rank], args.dim, 1234 + rank, dev),
+                                                row_offset=offs[rank]))
     enc = BertEncoderB200.random_init(EncoderConfig.bge_large(), seed=0, device=dev)
     rcfg = EncoderConfig(1024, 24, 16, 4096, args.rerank_vocab, max_position_embeddings=514, type_vocab_size=1,
                          layer_norm_eps=1e-5, position_offset=2)
@@ -68,7 +79,10 @@ def main():
         pairs = [[0] + rng.integers(5, args.rerank_vocab, args.pair_tokens - 2).tolist() + [2]
                  for _ in range(args.nq * args.k)]
         ev[3].record(st)
-        logits = reranker.score_token_lists(pairs)                           # H2D ids, D2H logits inside
+        if world == 1:
+            logits = reranker.score_token_lists(pairs)                       # H2D ids, D2H logits inside
+        else:
+            logits = sharded_rerank(reranker.score_token_lists, pairs, device=dev).cpu().numpy()
         ev[4].record(st)
         return ids_host, logits
 
@@ -77,21 +91,35 @@ def main():
 
     for _ in range(max(args.warmup, 1)):
         cycle(events())
-    torch.cuda.synchronize()
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
     all_ev = [events() for _ in range(args.cycles)]
     t0 = time.perf_counter()
     for ev in all_ev:
         ids_host, logits = cycle(ev)
-    torch.cuda.synchronize()
+    barrier()
     wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([wall], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
     stage = np.zeros(4)
     for ev in all_ev:
         stage += [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
     stage /= args.cycles
     assert ids_host.shape == (args.nq, args.k) and logits.shape == (args.nq * args.k, 1) and np.isfinite(logits).all()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
     print(json.dumps({
+        "n_gpus": world,
         "workload": f"{args.nq} probes x {args.cycles} cycles, {args.rows}x{args.dim} bf16 index top-{args.k}, "
-                    f"rerank {args.nq * args.k} pairs x {args.pair_tokens} tokens (XLM-R-large shape), 1 GPU",
+                    f"rerank {args.nq * args.k} pairs x {args.pair_tokens} tokens (XLM-R-large shape), {world} GPU(s)",
         "ms_per_cycle": {"encode_probes": round(float(stage[0]), 3), "search_and_ids_d2h": round(float(stage[1]), 3),
                          "host_pair_assembly": round(float(stage[2]), 3), "rerank": round(float(stage[3]), 3)},
         "wall_ms_per_cycle": round(wall * 1e3 / args.cycles, 3),
