@@ -55,12 +55,28 @@ struct SearchLayout {
   }
 };
 
-template <int KLIST, int CAP, int STAGES>
+// IVF variant of the scan (BASELINE config 4; semantic: oracle/ivf_oracle.py): the shard holds bf16 RESIDUALS grouped
+// by coarse list, every list padded to whole 128-row tiles, and a pass touches only the tiles of probed lists.
+//   work[i]   = (first stored row of the tile, valid rows in it, list id, 0), written by ivf_plan_kernel
+//   n_work    = number of work items (device scalar: the plan is built on the device, no host round trip)
+//   list_mask = per list, bit q set when query q probes it; coarse[list * 32 + q] = q . c_list from the coarse pass
+// The flat instantiations (IVF = false) take an empty struct instead and compile to the same SASS as before.
+struct IvfArgs {
+  const int4* work;
+  const int* n_work;
+  const uint32_t* list_mask;
+  const float* coarse;
+};
+struct NoIvfArgs {};
+template <bool IVF> struct IvfParam { using type = NoIvfArgs; };
+template <> struct IvfParam<true> { using type = IvfArgs; };
+
+template <int KLIST, int CAP, int STAGES, bool IVF = false>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_constant__ CUtensorMap tm_q,
                    int n_rows, int num_kb, int nq, int k, const uint64_t* __restrict__ after_keys,
                    const float* __restrict__ thr_floor, int floor_stride, uint64_t* __restrict__ part_keys,
-                   float* __restrict__ part_minmax) {
+                   float* __restrict__ part_minmax, const typename IvfParam<IVF>::type ivf) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -84,7 +100,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = (n_rows + kTileRows - 1) / kTileRows;
+  int num_tiles;
+  if constexpr (IVF) num_tiles = __ldg(ivf.n_work);
+  else num_tiles = (n_rows + kTileRows - 1) / kTileRows;
 
   // ------------------------------------------------------------ one-time setup
   if (warp == 0 && lane == 0) {
@@ -138,8 +156,10 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bar_full[stage], kStageBytes);
-          tma_load_2d_hint(&tm_corpus, &bar_full[stage], stage_base + stage * kStageBytes, kb * kBlockK,
-                           tile * kTileRows, pol);
+          int tile_row0;
+          if constexpr (IVF) tile_row0 = __ldg(&ivf.work[tile].x);
+          else tile_row0 = tile * kTileRows;
+          tma_load_2d_hint(&tm_corpus, &bar_full[stage], stage_base + stage * kStageBytes, kb * kBlockK, tile_row0, pol);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -184,7 +204,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
     for (int q = 0; q < kNQ; ++q) { mn[q] = INFINITY; mx[q] = -INFINITY; }
 
     // direct first tile needs room for 128 keys per query and no admission bound of any kind
-    const bool direct_first = (KLIST + CAP >= 128) && thr_floor == nullptr && after_keys == nullptr;
+    const bool direct_first = !IVF && (KLIST + CAP >= 128) && thr_floor == nullptr && after_keys == nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -198,17 +218,40 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       if (lane == 0) mbar_arrive(&bar_tempty[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
 
-      const int row = tile * kTileRows + quad * 32 + lane;
+      int row;
       uint32_t pending = 0;
-      if (row < n_rows) {
+      if constexpr (!IVF) {
+        row = tile * kTileRows + quad * 32 + lane;
+        if (row < n_rows) {
 #pragma unroll
-        for (int q = 0; q < kNQ; ++q) {
-          const float s = __uint_as_float(r[q]);
-          mn[q] = fminf(mn[q], s);
-          mx[q] = fmaxf(mx[q], s);
-          if (s >= thr_f[q] && s <= bnd_f[q]) pending |= 1u << q;
+          for (int q = 0; q < kNQ; ++q) {
+            const float s = __uint_as_float(r[q]);
+            mn[q] = fminf(mn[q], s);
+            mx[q] = fmaxf(mx[q], s);
+            if (s >= thr_f[q] && s <= bnd_f[q]) pending |= 1u << q;
+          }
+          if (nq < kNQ) pending &= (1u << nq) - 1u;
         }
-        if (nq < kNQ) pending &= (1u << nq) - 1u;
+      } else {
+        // this tile belongs to ONE coarse list: only the queries probing it see its rows, and a row's score is
+        // q . c_list (coarse pass, fp32) + q . residual (this tile's UMMA)
+        const int4 item = __ldg(&ivf.work[tile]);
+        row = item.x + quad * 32 + lane;
+        if (quad * 32 + lane < item.y) {
+          const uint32_t probing = __ldg(&ivf.list_mask[item.z]);
+          const float* co = ivf.coarse + size_t(item.z) * kNQ;
+#pragma unroll
+          for (int q = 0; q < kNQ; ++q) {
+            if ((probing >> q) & 1u) {
+              const float s = __uint_as_float(r[q]) + __ldg(co + q);
+              r[q] = __float_as_uint(s);
+              mn[q] = fminf(mn[q], s);
+              mx[q] = fmaxf(mx[q], s);
+              if (s >= thr_f[q] && s <= bnd_f[q]) pending |= 1u << q;
+            }
+          }
+          if (nq < kNQ) pending &= (1u << nq) - 1u;
+        }
       }
       // First tile of an unseeded pass: the lists are empty and every row is a candidate.  Skip the reservation
       // protocol (128-way contended atomics, several flush rounds): each row's key goes straight to slot
@@ -305,6 +348,49 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// Builds one IVF pass's plan on the device (single CTA): which queries probe which list, their coarse terms, and the
+// work-list of the probed lists' tiles.  probed_ids / probed_scores are the coarse top-nprobe of each query
+// (crag_search_topk over the centroid table; id -1 = fewer than nprobe lists).
+__global__ void __launch_bounds__(1024) ivf_plan_kernel(const int64_t* __restrict__ probed_ids,
+                                                        const float* __restrict__ probed_scores, int nq, int nprobe,
+                                                        int nlist, const int32_t* __restrict__ list_tile_start,
+                                                        const int32_t* __restrict__ list_rows,
+                                                        uint32_t* __restrict__ list_mask, float* __restrict__ coarse,
+                                                        int4* __restrict__ work, int* __restrict__ n_work) {
+  __shared__ int s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  for (int l = threadIdx.x; l < nlist; l += blockDim.x) list_mask[l] = 0u;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nq * nprobe; i += blockDim.x) {
+    const int64_t l = probed_ids[i];
+    if (l < 0 || l >= nlist) continue;
+    const int q = i / nprobe;
+    atomicOr(&list_mask[l], 1u << q);
+    coarse[size_t(l) * kNQ + q] = probed_scores[i];
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < nlist; l += blockDim.x) {
+    const int rows = list_rows[l];
+    if (list_mask[l] == 0u || rows <= 0) continue;
+    const int tiles = (rows + kTileRows - 1) / kTileRows;
+    const int at = atomicAdd(&s_count, tiles);
+    const int t0 = list_tile_start[l];
+    for (int j = 0; j < tiles; ++j)
+      work[at + j] = make_int4((t0 + j) * kTileRows, min(kTileRows, rows - j * kTileRows), l, 0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *n_work = s_count;
+}
+
+// stored-row ids of the merged answer -> the rows' original ids (-1 stays -1)
+__global__ void ivf_map_ids_kernel(int64_t* __restrict__ ids, int n, const int64_t* __restrict__ row_ids) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int64_t v = ids[i];
+    ids[i] = v >= 0 ? row_ids[v] : -1;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -468,7 +554,19 @@ int launch_search(const CUtensorMap& tm_corpus, const CUtensorMap& tm_q, int n_r
   auto kern = search_topk_kernel<KLIST, CAP, STAGES>;
   CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, n_rows, num_kb, nq, k, after_keys, thr_floor, floor_stride,
-                                               part_keys, part_minmax);
+                                               part_keys, part_minmax, NoIvfArgs{});
+  CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
+}
+
+template <int KLIST, int CAP, int STAGES>
+int launch_ivf_scan(const CUtensorMap& tm_res, const CUtensorMap& tm_q, int num_kb, int nq, int k, int grid,
+                    uint64_t* part_keys, float* part_minmax, const IvfArgs& ivf, cudaStream_t stream) {
+  using L = SearchLayout<KLIST, CAP, STAGES>;
+  const size_t smem = L::smem_bytes(num_kb);
+  auto kern = search_topk_kernel<KLIST, CAP, STAGES, true>;
+  CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  kern<<<grid, kSearchThreads, smem, stream>>>(tm_res, tm_q, 0, num_kb, nq, k, nullptr, nullptr, 0, part_keys, part_minmax, ivf);
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }
@@ -528,9 +626,8 @@ int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_st
 }
 
 // merge the per-CTA partials of one pass into the final (ids, scores, minmax) of its <= 32 queries
-int finalize_pass(const void* workspace, int64_t n_rows, int nq, int k, int64_t row_offset, int64_t* out_ids,
-                  float* out_scores, float* out_minmax, uint64_t* last_keys, const SearchPlan& plan, cudaStream_t stream) {
-  const int grid = scan_grid(n_rows, plan);
+int finalize_parts(const void* workspace, int grid, int nq, int k, int64_t row_offset, int64_t* out_ids,
+                   float* out_scores, float* out_minmax, uint64_t* last_keys, const SearchPlan& plan, cudaStream_t stream) {
   const uint64_t* part_keys = static_cast<const uint64_t*>(workspace);
   const float* part_minmax = reinterpret_cast<const float*>(static_cast<const uint8_t*>(workspace) + plan.keys_bytes);
   const int mgrid = nq;  // one CTA per query
@@ -544,8 +641,84 @@ int finalize_pass(const void* workspace, int64_t n_rows, int nq, int k, int64_t 
   return CRAG_OK;
 }
 
+int finalize_pass(const void* workspace, int64_t n_rows, int nq, int k, int64_t row_offset, int64_t* out_ids,
+                  float* out_scores, float* out_minmax, uint64_t* last_keys, const SearchPlan& plan, cudaStream_t stream) {
+  return finalize_parts(workspace, scan_grid(n_rows, plan), nq, k, row_offset, out_ids, out_scores, out_minmax, last_keys,
+                        plan, stream);
+}
+
+// IVF workspace = the flat scan's per-CTA partials, then the per-pass plan
+struct IvfPlan {
+  size_t mask_off, coarse_off, work_off, count_off, total;
+};
+IvfPlan plan_ivf(const SearchPlan& sp, int nlist, int64_t total_tiles) {
+  auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+  IvfPlan p;
+  p.mask_off = sp.keys_bytes + sp.minmax_bytes;
+  p.coarse_off = p.mask_off + up(size_t(nlist) * 4);
+  p.work_off = p.coarse_off + up(size_t(nlist) * kNQ * 4);
+  p.count_off = p.work_off + up(size_t(total_tiles) * sizeof(int4));
+  p.total = p.count_off + 256;
+  return p;
+}
+
 }  // namespace
 }  // namespace crag
+
+extern "C" size_t crag_ivf_workspace_bytes(int nlist, int64_t total_tiles, int k) {
+  if (nlist < 1 || total_tiles < 0 || k < 1 || k > 128) return 0;
+  return plan_ivf(plan_search(k), nlist, total_tiles).total;
+}
+
+extern "C" int crag_ivf_search(const void* residuals, int64_t n_rows_padded, int dim, int64_t row_stride,
+                               const int32_t* list_tile_start, const int32_t* list_rows, int nlist,
+                               int64_t total_tiles, const int64_t* row_ids, const void* queries, int nq,
+                               const int64_t* probed_ids, const float* probed_scores, int nprobe, int k,
+                               int64_t* out_ids, float* out_scores, float* out_minmax, void* workspace,
+                               size_t workspace_bytes, crag_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const SearchPlan sp = plan_search(k >= 1 && k <= 128 ? k : 1);
+  if (nlist < 1 || nlist > (1 << 20) || nprobe < 1 || nprobe > nlist) return fail(CRAG_ERR_INVALID, "ivf: need 1 <= nprobe <= nlist <= 2^20 (nprobe=%d nlist=%d)", nprobe, nlist);
+  if (total_tiles < 0 || total_tiles * kTileRows != n_rows_padded) return fail(CRAG_ERR_INVALID, "ivf: n_rows_padded (%lld) must be total_tiles (%lld) * %d", (long long)n_rows_padded, (long long)total_tiles, kTileRows);
+  const IvfPlan ip = plan_ivf(sp, nlist, total_tiles);
+  int rc = check_search_args(residuals, n_rows_padded, dim, row_stride, queries, nq, k, workspace, workspace_bytes, sp);
+  if (rc != CRAG_OK) return rc;
+  if (workspace_bytes < ip.total) return fail(CRAG_ERR_WORKSPACE, "ivf: workspace %zu < %zu bytes", workspace_bytes, ip.total);
+  if (!list_tile_start || !list_rows || !row_ids || !probed_ids || !probed_scores || !out_ids || !out_scores) return fail(CRAG_ERR_INVALID, "ivf: null pointer");
+  if (n_rows_padded == 0) return fail(CRAG_ERR_INVALID, "ivf: empty index");
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint64_t* part_keys = reinterpret_cast<uint64_t*>(ws);
+  float* part_minmax = reinterpret_cast<float*>(ws + sp.keys_bytes);
+  IvfArgs ivf;
+  ivf.list_mask = reinterpret_cast<uint32_t*>(ws + ip.mask_off);
+  ivf.coarse = reinterpret_cast<float*>(ws + ip.coarse_off);
+  ivf.work = reinterpret_cast<int4*>(ws + ip.work_off);
+  ivf.n_work = reinterpret_cast<int*>(ws + ip.count_off);
+  CUtensorMap tm_res;
+  rc = make_tmap_bf16_2d(&tm_res, residuals, uint64_t(n_rows_padded), uint64_t(dim), uint64_t(row_stride) * 2, kTileRows);
+  if (rc != CRAG_OK) return rc;
+  const int num_kb = dim / kBlockK;
+  for (int q0 = 0; q0 < nq; q0 += kNQ) {
+    const int nqc = (nq - q0) < kNQ ? (nq - q0) : kNQ;
+    CUtensorMap tm_q;
+    rc = make_tmap_bf16_2d(&tm_q, static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2, uint64_t(nqc), uint64_t(dim), uint64_t(dim) * 2, kNQ);
+    if (rc != CRAG_OK) return rc;
+    ivf_plan_kernel<<<1, 1024, 0, stream>>>(probed_ids + size_t(q0) * nprobe, probed_scores + size_t(q0) * nprobe, nqc, nprobe,
+                                            nlist, list_tile_start, list_rows, const_cast<uint32_t*>(ivf.list_mask),
+                                            const_cast<float*>(ivf.coarse), const_cast<int4*>(ivf.work), const_cast<int*>(ivf.n_work));
+    CRAG_CUDA_OK(cudaGetLastError());
+    // every CTA of the grid publishes a (possibly empty) partial list, so the merge always reads sp.grid parts
+    rc = (k <= 64) ? launch_ivf_scan<64, 64, 7>(tm_res, tm_q, num_kb, nqc, k, sp.grid, part_keys, part_minmax, ivf, stream)
+                   : launch_ivf_scan<128, 128, 5>(tm_res, tm_q, num_kb, nqc, k, sp.grid, part_keys, part_minmax, ivf, stream);
+    if (rc != CRAG_OK) return rc;
+    rc = finalize_parts(workspace, sp.grid, nqc, k, 0, out_ids + size_t(q0) * k, out_scores + size_t(q0) * k,
+                        out_minmax ? out_minmax + size_t(q0) * 2 : nullptr, nullptr, sp, stream);
+    if (rc != CRAG_OK) return rc;
+    ivf_map_ids_kernel<<<(nqc * k + 255) / 256, 256, 0, stream>>>(out_ids + size_t(q0) * k, nqc * k, row_ids);
+    CRAG_CUDA_OK(cudaGetLastError());
+  }
+  return CRAG_OK;
+}
 
 extern "C" int crag_search_scan(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride,
                                 const void* queries, int nq, int k, void* workspace, size_t workspace_bytes,
@@ -608,6 +781,7 @@ extern "C" int crag_search_topk_after(const void* corpus, int64_t n_rows, int di
     }
     rc = scan_pass(corpus, n_rows, dim, corpus_row_stride, qptr, nqc, k, after_keys ? after_keys + q0 : nullptr, floor, k,
                    workspace, plan, stream);
+    if (rc != CRAG_OK) return rc;
     rc = finalize_pass(workspace, n_rows, nqc, k, row_offset, out_ids + size_t(q0) * k, out_scores + size_t(q0) * k,
                        out_minmax ? out_minmax + size_t(q0) * 2 : nullptr, last_keys ? last_keys + q0 : nullptr, plan, stream);
     if (rc != CRAG_OK) return rc;

@@ -150,6 +150,28 @@ CRAG_API int crag_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t l
                             const void* residual, int64_t ldr, void* out, int64_t ldo, int m, int n, int k,
                             int epilogue, crag_stream_t stream);
 
+/* IVF residual inner-product search (BASELINE config 4: "IVF-4096 coarse quantizer + fused residual-IP top-100").
+ * The reference has no IVF / ANN code (faiss-cpu is pinned at requirements.txt:34 and never imported), so this
+ * entry point replaces nothing of the reference's; its semantic is fixed by oracle/ivf_oracle.py.
+ *
+ * Shard layout (device): `residuals` bf16 [n_rows_padded, dim] = x - c_list grouped by coarse list, every list
+ * padded with zero rows to whole 128-row tiles; list l owns tiles [list_tile_start[l], list_tile_start[l+1]) and
+ * its first list_rows[l] rows are real; row_ids[stored row] = the row's original id (padding: -1).
+ * The caller runs the coarse pass itself (crag_search_topk over the bf16 centroid table with k = nprobe) and
+ * passes its output: probed_ids int64 [nq, nprobe] (-1 = absent), probed_scores fp32 [nq, nprobe] = q . c_list.
+ * Per block of 32 queries: a plan kernel marks which queries probe which list and compacts the probed lists'
+ * tiles into a work-list; the scan kernel (the flat kernel's TMA/tcgen05/selector pipeline walking that work-list)
+ * scores  q . c_list + q . residual  for the probing queries only; the per-CTA lists are merged and stored-row ids
+ * mapped to original ids.  Outputs as crag_search_topk (min/max range over the probed rows).
+ * workspace >= crag_ivf_workspace_bytes(nlist, total_tiles, k), 256-byte aligned. */
+CRAG_API size_t crag_ivf_workspace_bytes(int nlist, int64_t total_tiles, int k);
+CRAG_API int crag_ivf_search(const void* residuals, int64_t n_rows_padded, int dim, int64_t row_stride,
+                             const int32_t* list_tile_start, const int32_t* list_rows, int nlist,
+                             int64_t total_tiles, const int64_t* row_ids, const void* queries, int nq,
+                             const int64_t* probed_ids, const float* probed_scores, int nprobe, int k,
+                             int64_t* out_ids, float* out_scores, float* out_minmax, void* workspace,
+                             size_t workspace_bytes, crag_stream_t stream);
+
 /* Encoder weights (BERT-family, post-LN; HF BertModel parameter names in
  * comments).  Matrices are device bf16 in torch.nn.Linear layout [out, in];
  * biases and LayerNorm parameters are device fp32.  The struct itself and the

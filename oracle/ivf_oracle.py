@@ -67,10 +67,12 @@ def assign(x: np.ndarray, centroids: np.ndarray) -> np.ndarray:
 class IVFLists:
     """The layout the engine's IVF shard uses: rows grouped by list, back to back."""
 
-    def __init__(self, x: np.ndarray, centroids: np.ndarray):
+    def __init__(self, x: np.ndarray, centroids: np.ndarray, assignment: np.ndarray = None):
+        """`assignment` overrides assign(): parity tests of the SEARCH pass it the engine's own row -> list map, so
+        that a row sitting on a float tie between two centroids does not turn into a search mismatch."""
         x = np.asarray(x, dtype=np.float32)
         self.centroids = bf16_round(centroids)                     # what the coarse pass sees
-        a = assign(x, centroids)
+        a = assign(x, centroids) if assignment is None else np.asarray(assignment, dtype=np.int64)
         order = np.lexsort((np.arange(x.shape[0]), a))             # list id, then original id
         self.ids = order.astype(np.int64)                          # original id of each stored row
         self.list_of_row = a[order]
@@ -95,12 +97,14 @@ def probe_lists(lists: IVFLists, queries: np.ndarray, nprobe: int) -> Tuple[np.n
     return order.astype(np.int64), np.take_along_axis(s, order, axis=1)
 
 
-def search(lists: IVFLists, queries: np.ndarray, nprobe: int, k: int):
+def search(lists: IVFLists, queries: np.ndarray, nprobe: int, k: int, probed=None):
     """-> (ids int64 [nq, k], scores float64 [nq, k], gaps float64 [nq, k]); id -1 / score -inf where the probed
-    lists hold fewer than k rows.  gaps as in search_oracle.topk_exact (near ties are compared as sets)."""
+    lists hold fewer than k rows.  gaps as in search_oracle.topk_exact (near ties are compared as sets).
+    `probed = (list ids [nq, nprobe], coarse scores)` replaces the coarse pass (ids < 0 are skipped): the fine
+    pass can then be checked on exactly the lists, and with exactly the fp32 coarse terms, the engine used."""
     q = bf16_round(queries).astype(np.float64)
     nq = q.shape[0]
-    probed, coarse = probe_lists(lists, queries, min(nprobe, lists.nlist))
+    probed, coarse = probe_lists(lists, queries, min(nprobe, lists.nlist)) if probed is None else probed
     out_i = np.full((nq, k), -1, dtype=np.int64)
     out_s = np.full((nq, k), -np.inf)
     gaps = np.full((nq, k), np.inf)
@@ -108,6 +112,8 @@ def search(lists: IVFLists, queries: np.ndarray, nprobe: int, k: int):
         cand_i: List[np.ndarray] = []
         cand_s: List[np.ndarray] = []
         for l, cs in zip(probed[i], coarse[i]):
+            if l < 0:
+                continue
             a, b = lists.offsets[l], lists.offsets[l + 1]
             if b > a:
                 cand_i.append(lists.ids[a:b])

@@ -160,3 +160,33 @@ def test_cross_encoder_reranker_host_logic():
     o = np.argsort(-s.astype(np.float64), kind="stable")[:2]
     assert idx == [[7, 8, 9][i] for i in o] and kept == [items[i] for i in o] and len(meta["confidence"]) == 2
     assert flt("q", [], [], 5) == ([], [], {"confidence": None})
+
+
+def test_ivf_layout_is_list_major_and_tile_aligned():
+    """comorag_b200.ivf.ivf_layout against the oracle's grouping: same (list, id) order, every list starting on a
+    128-row tile, destinations unique, empty lists taking no tile."""
+    import torch
+    from comorag_b200.ivf import TILE_ROWS, ivf_layout
+    from oracle import ivf_oracle as ivf
+    rng = np.random.default_rng(3)
+    n, nlist = 5000, 37
+    a = rng.integers(0, nlist, n)
+    a[a == 5] = 6                                                   # list 5 is empty
+    a[:300] = 9                                                     # list 9 spans several tiles
+    order, dest, tile_start, list_rows = ivf_layout(torch.from_numpy(a), nlist)
+    order, dest, tile_start, list_rows = order.numpy(), dest.numpy(), tile_start.numpy(), list_rows.numpy()
+    np.testing.assert_array_equal(order, np.lexsort((np.arange(n), a)))
+    np.testing.assert_array_equal(list_rows, np.bincount(a, minlength=nlist))
+    assert tile_start[0] == 0 and tile_start[6] == tile_start[5]    # the empty list owns no tile
+    np.testing.assert_array_equal(np.diff(tile_start), (list_rows + TILE_ROWS - 1) // TILE_ROWS)
+    assert len(set(dest.tolist())) == n and dest.max() < tile_start[-1] * TILE_ROWS
+    for l in range(nlist):
+        mine = dest[a[order] == l]
+        np.testing.assert_array_equal(mine, tile_start[l] * TILE_ROWS + np.arange(list_rows[l]))
+    # the oracle's back-to-back layout is the same order without the padding
+    x = rng.standard_normal((n, 8)).astype(np.float32)
+    c = rng.standard_normal((nlist, 8)).astype(np.float32)
+    L = ivf.IVFLists(x, c, assignment=a)
+    np.testing.assert_array_equal(L.ids, order)
+    with pytest.raises(ValueError):
+        ivf_layout(torch.tensor([0, 99]), 4)
