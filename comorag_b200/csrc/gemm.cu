@@ -388,7 +388,10 @@ struct Gemm2Layout {
   }
 };
 
-template <int BN, int STAGES, int EPI, int EPI_WARPS>
+// PIPE = true (A/B variant, bit 2 of the variant word; not dispatched by default and NOT yet validated on hardware):
+// the epilogue keeps the NEXT 32-column tcgen05.ld in flight while it works on the current chunk (two register
+// buffers) instead of exposing the TMEM read latency once per chunk.
+template <int BN, int STAGES, int EPI, int EPI_WARPS, bool PIPE = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
                   int K, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, int64_t ldr,
@@ -497,12 +500,28 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + col_begin;
+      if constexpr (!PIPE) {
 #pragma unroll 1
       for (int c = 0; c < kColsPerWarp / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c * 32, r);
         tmem_ld_wait();
         epilogue_chunk_staged<EPI>(r, row, row_base, n0 + c * 32, M, N, bias, residual, ldr, out, ldo, stage, lane);
+      }
+      } else {
+        constexpr int kChunks = kColsPerWarp / 32;
+        static_assert(kChunks % 2 == 0, "the pipelined epilogue walks the chunks in pairs");
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32b_x32(t_addr, ra);
+#pragma unroll 1
+        for (int c = 0; c < kChunks; c += 2) {
+          tmem_ld_wait_regs(ra);                                   // chunk c has landed
+          tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, rb);          // chunk c+1 in flight during chunk c's math
+          epilogue_chunk_staged<EPI>(ra, row, row_base, n0 + c * 32, M, N, bias, residual, ldr, out, ldo, stage, lane);
+          tmem_ld_wait_regs(rb);
+          if (c + 2 < kChunks) tmem_ld_32x32b_x32(t_addr + (c + 2) * 32, ra);
+          epilogue_chunk_staged<EPI>(rb, row, row_base, n0 + (c + 1) * 32, M, N, bias, residual, ldr, out, ldo, stage, lane);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -520,12 +539,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (warp == 1) tmem_dealloc_2cta(tmem_base, kTmemCols);
 }
 
-template <int BN, int STAGES, int EPI, int EPI_WARPS>
+template <int BN, int STAGES, int EPI, int EPI_WARPS, bool PIPE = false>
 static int launch_gemm2_t(const CUtensorMap& tm_a, const CUtensorMap& tm_b, int M, int N, int K, const float* bias,
                           const __nv_bfloat16* residual, int64_t ldr, __nv_bfloat16* out, int64_t ldo,
                           cudaStream_t stream) {
   using L = Gemm2Layout<BN, STAGES>;
-  auto kern = gemm2_bf16_kernel<BN, STAGES, EPI, EPI_WARPS>;
+  auto kern = gemm2_bf16_kernel<BN, STAGES, EPI, EPI_WARPS, PIPE>;
   CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L::smem_bytes(EPI_WARPS))));
   const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
   int sms = sm_count();
@@ -537,14 +556,14 @@ static int launch_gemm2_t(const CUtensorMap& tm_a, const CUtensorMap& tm_b, int 
   return CRAG_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PIPE = false>
 static int launch_gemm2_e(int epi, const CUtensorMap& tm_a, const CUtensorMap& tm_b, int M, int N, int K,
                           const float* bias, const __nv_bfloat16* residual, int64_t ldr, __nv_bfloat16* out,
                           int64_t ldo, cudaStream_t stream) {
   switch (epi) {
-    case GEMM_EPI_BIAS: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS, 4>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
-    case GEMM_EPI_BIAS_GELU: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS_GELU, 8>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
-    case GEMM_EPI_BIAS_RESIDUAL: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS_RESIDUAL, 8>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
+    case GEMM_EPI_BIAS: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS, 4, PIPE>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
+    case GEMM_EPI_BIAS_GELU: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS_GELU, 8, PIPE>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
+    case GEMM_EPI_BIAS_RESIDUAL: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS_RESIDUAL, 8, PIPE>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
   }
   return fail(CRAG_ERR_INVALID, "gemm: unknown epilogue %d", epi);
 }
@@ -567,6 +586,10 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const floa
     // CTA-pair kernel: each CTA fetches half of the W tile
     rc = make_tmap_bf16_2d(&tm_b, w, uint64_t(N), uint64_t(K), uint64_t(ldw) * 2, wide ? 128 : 64);
     if (rc != CRAG_OK) return rc;
+    if (variant & 4) {  // A/B switch: pipelined TMEM reads in the epilogue
+      if (wide) return launch_gemm2_e<256, 6, true>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
+      return launch_gemm2_e<128, 8, true>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
+    }
     if (wide) return launch_gemm2_e<256, 6>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
     return launch_gemm2_e<128, 8>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
   }
@@ -581,7 +604,8 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const floa
 extern "C" int crag_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias,
                               const void* residual, int64_t ldr, void* out, int64_t ldo, int m, int n, int k,
                               int epilogue, crag_stream_t stream) {
-  // bits 8+ of `epilogue` select a kernel variant for A/B testing (0 = default dispatch, 1 = force single-CTA)
+  // bits 8+ of `epilogue` select a kernel variant for A/B testing: 0 = default dispatch, bit 0 = force single-CTA,
+  // bit 1 = force the BN = 128 tile, bit 2 = pipelined TMEM reads in the CTA-pair epilogue (unvalidated)
   return crag::gemm_bf16(a, lda, w, ldw, bias, residual, ldr, out, ldo, m, n, k, epilogue & 0xFF,
                          static_cast<cudaStream_t>(stream), epilogue >> 8);
 }

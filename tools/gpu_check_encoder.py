@@ -14,13 +14,16 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GEMM_CASES = [  # M, N, K, epi, variant (0 = default dispatch: CTA-pair kernel when M > 128; 1 = force single-CTA)
+GEMM_CASES = [  # M, N, K, epi, variant (0 = default dispatch: CTA-pair kernel when M > 128; bit 0 = force single-CTA,
+    # bit 1 = force BN 128, bit 2 = pipelined TMEM reads in the CTA-pair epilogue -- not validated yet)
     (128, 128, 64, 0, 0), (129, 256, 128, 0, 0), (255, 128, 64, 2, 0), (257, 384, 384, 1, 0), (300, 384, 384, 0, 0),
     (1000, 1152, 384, 0, 0), (777, 1536, 384, 1, 0), (512, 384, 1536, 2, 0),
     (16384, 3072, 1024, 0, 0), (16384, 3072, 1024, 0, 1), (16384, 1024, 1024, 2, 0), (16384, 1024, 1024, 2, 1),
     (16384, 4096, 1024, 1, 0), (16384, 4096, 1024, 1, 1), (16384, 1024, 4096, 2, 0), (16384, 1024, 4096, 2, 1),
     (16384, 1152, 384, 0, 0), (16384, 384, 1536, 2, 0), (16384, 768, 3072, 2, 0),
     (16384, 1024, 1024, 2, 2), (16384, 1024, 4096, 2, 2), (16384, 3072, 1024, 0, 2), (16384, 768, 768, 2, 0), (16384, 768, 768, 2, 2),
+    (257, 384, 384, 1, 4), (1000, 1152, 384, 0, 4), (512, 384, 1536, 2, 4),
+    (16384, 3072, 1024, 0, 4), (16384, 1024, 1024, 2, 4), (16384, 4096, 1024, 1, 4), (16384, 1024, 4096, 2, 4),
 ]
 ATTN_CASES = [  # H, heads, lengths, tc (1 = tcgen05 kernel)
     (128, 4, [5, 64, 65, 1, 130], 0), (1024, 16, [512, 33, 200, 512], 0), (384, 12, [77, 512, 300], 0), (768, 12, [128] * 6, 0),
