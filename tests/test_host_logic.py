@@ -190,3 +190,41 @@ def test_ivf_layout_is_list_major_and_tile_aligned():
     np.testing.assert_array_equal(L.ids, order)
     with pytest.raises(ValueError):
         ivf_layout(torch.tensor([0, 99]), 4)
+
+
+def test_shard_bounds_and_packed_records_properties():
+    """Property checks (hypothesis) of the host-side index arithmetic the multi-GPU path relies on."""
+    from hypothesis import given, settings, strategies as st
+    from comorag_b200.dist import pack_partial, shard_bounds, unpack_partials
+    from comorag_b200.index import packed_record_bytes, packed_views
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 10**9), st.integers(1, 64))
+    def bounds(n, world):
+        b = shard_bounds(n, world)
+        sizes = np.diff(b)
+        assert b[0] == 0 and b[-1] == n and len(b) == world + 1
+        assert sizes.min() >= 0 and sizes.max() - sizes.min() <= 1 and np.all(np.diff(sizes) <= 0)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 128), st.integers(1, 5))
+    def records(nq, k, world):
+        per = packed_record_bytes(nq, k)
+        assert per % 16 == 0 and per >= nq * k * 12 + nq * 8
+        g = torch.Generator().manual_seed(nq * 1000 + k)
+        parts = []
+        for r in range(world):
+            ids = torch.randint(-1, 10**12, (nq, k), generator=g)
+            sc = torch.randn(nq, k, generator=g)
+            mm = torch.randn(nq, 2, generator=g)
+            buf = pack_partial(ids, sc, mm)
+            assert buf.numel() == per
+            v = packed_views(buf, nq, k)
+            assert torch.equal(v[0], ids) and torch.equal(v[1], sc) and torch.equal(v[2], mm)
+            parts.append((ids, sc, mm, buf))
+        gi, gs, gm = unpack_partials(torch.cat([p[3] for p in parts]), world, nq, k)
+        for r, (ids, sc, mm, _) in enumerate(parts):
+            assert torch.equal(gi[r], ids) and torch.equal(gs[r], sc) and torch.equal(gm[r], mm)
+
+    bounds()
+    records()
