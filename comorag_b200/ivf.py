@@ -88,6 +88,7 @@ def assign_rows(x: torch.Tensor, centroids_bf16: torch.Tensor, block: int = 1 <<
 class IVFIndex:
     def __init__(self, centroids_bf16: torch.Tensor, residuals: torch.Tensor, row_ids: torch.Tensor,
                  list_tile_start: torch.Tensor, list_rows: torch.Tensor, n_rows: int):
+        """row_ids carry GLOBAL ids: a rank of a row-sharded index builds with row_offset = its first global row."""
         self.device = residuals.device
         self.dim = residuals.shape[1]
         self.nlist = centroids_bf16.shape[0]
@@ -100,9 +101,10 @@ class IVFIndex:
 
     @classmethod
     def build(cls, rows: torch.Tensor, nlist: int, iters: int = 10, seed: int = 0, centroids: Optional[torch.Tensor] = None,
-              train_rows: int = 1 << 20) -> "IVFIndex":
+              train_rows: int = 1 << 20, row_offset: int = 0) -> "IVFIndex":
         """rows: CUDA float [n, dim] (dim % 64 == 0), unit-norm.  Trains `nlist` centroids on a sample (unless
-        given), assigns every row, and lays the residuals out by list."""
+        given), assigns every row, and lays the residuals out by list.  `row_offset` = global id of rows[0]
+        (row-sharded index: every rank passes the SAME centroids and its own offset)."""
         if not rows.is_cuda or rows.dim() != 2 or rows.shape[1] % 64 != 0 or rows.shape[1] > 1024:
             raise ValueError("IVFIndex.build expects a CUDA [n, dim] tensor with dim % 64 == 0 and dim <= 1024")
         n, dim = rows.shape
@@ -122,7 +124,7 @@ class IVFIndex:
         for s in range(0, n, block):
             o, d = order[s:s + block], dest[s:s + block]
             residuals[d] = (rows[o].float() - cf[assignment[o]]).to(torch.bfloat16)
-            row_ids[d] = o
+            row_ids[d] = o + int(row_offset)
         self = cls(c_bf16, residuals[:total] if total else residuals[:0], row_ids[:total] if total else row_ids[:0],
                    tile_start.contiguous(), list_rows.contiguous(), n)
         self.assignment = assignment
@@ -168,3 +170,28 @@ class IVFIndex:
         q = q.to(self.device, non_blocking=True).to(torch.bfloat16)
         ids, scores, _, _ = self.search_device(q, nprobe, k)
         return ids.cpu().numpy(), scores.cpu().numpy()
+
+
+class ShardedIVF:
+    """One rank's handle on a row-sharded IVF index (BASELINE config 4 on the GPUs of one box): every rank holds the
+    SAME centroid table and the residual lists of its own rows, so all ranks probe the same lists; each searches its
+    shard, ONE all-gather of the packed (ids, scores, min/max) records and the merge kernel give every rank the
+    global answer -- the exchange step of the flat row-sharded index (dist.ShardedIndex), unchanged."""
+
+    def __init__(self, local: IVFIndex, group=None):
+        import torch.distributed as dist
+        self.local, self.group = local, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def search_device(self, queries_bf16: torch.Tensor, nprobe: int, k: int):
+        import torch.distributed as dist
+        from .dist import pack_partial
+        from .index import merge_topk_packed, packed_record_bytes
+        ids, scores, minmax, _ = self.local.search_device(queries_bf16, nprobe, k)
+        if self.world == 1:
+            return ids, scores, minmax
+        nq = queries_bf16.shape[0]
+        mine = pack_partial(ids, scores, minmax)
+        gathered = torch.empty(self.world * packed_record_bytes(nq, k), dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        return merge_topk_packed(gathered, self.world, nq, k)

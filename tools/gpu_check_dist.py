@@ -36,6 +36,22 @@ def main():
         flag = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         results.append({"shape": [n, dim, nq, k], "world": world, "all_ranks_equal_single_gpu": bool(flag.item())})
+    # row-sharded IVF (shared centroids, per-rank residual lists) == the single-GPU IVF over the whole corpus
+    from comorag_b200.ivf import IVFIndex, ShardedIVF, spherical_kmeans
+    for n, dim, nlist, nprobe, nq, k in [(60_000, 768, 64, 8, 32, 100), (9_000, 128, 32, 32, 5, 10)]:
+        corpus = make_unit_rows(n, dim, 81, device=dev).float()
+        queries = make_unit_rows(nq, dim, 82, device=dev)
+        cent = spherical_kmeans(corpus, nlist, iters=3, seed=0)       # same data + seed on every rank -> same table
+        offs = shard_bounds(n, world)
+        local = IVFIndex.build(corpus[offs[rank]:offs[rank + 1]].contiguous(), nlist, centroids=cent, row_offset=offs[rank])
+        ids, scores, mm = ShardedIVF(local).search_device(queries, nprobe, k)
+        w_ids, w_scores, w_mm, _ = IVFIndex.build(corpus, nlist, centroids=cent).search_device(queries, nprobe, k)
+        # ids may differ only inside exact score ties (stored order differs between the layouts)
+        same = (ids == w_ids) | (scores == torch.roll(scores, 1, 1)) | (scores == torch.roll(scores, -1, 1))
+        ok = bool(torch.equal(scores, w_scores) and bool(same.all()) and torch.equal(mm, w_mm))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        results.append({"ivf_shape": [n, dim, nlist, nprobe, nq, k], "world": world, "all_ranks_equal_single_gpu": bool(flag.item())})
     if rank == 0:
         print("RESULT " + json.dumps(results))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
