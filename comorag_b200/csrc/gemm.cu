@@ -161,12 +161,27 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
 // (full 32-byte sectors) instead of 32 rows x 16 B.  `stage` is this warp's private 32 x 80 B tile.
 constexpr int kEpiStagePitch = 80;
 constexpr int kEpiStageBytes = 32 * kEpiStagePitch;
-template <int EPI>
+// Residual vectors of one 32-column chunk of this thread's row, fetched ahead of use by the pipelined epilogue
+// (PIPE variant): 4 x 16 B, zero where the row / columns fall outside the matrix.
+struct ResidualChunk {
+  uint4 v[4];
+};
+__device__ __forceinline__ void load_residual_chunk(ResidualChunk& rc, const __nv_bfloat16* __restrict__ residual,
+                                                    int64_t ldr, int row, int col0, int M, int N) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    rc.v[v] = make_uint4(0u, 0u, 0u, 0u);
+    if (row < M && col0 + v * 8 < N)
+      rc.v[v] = *reinterpret_cast<const uint4*>(residual + int64_t(row) * ldr + col0 + v * 8);
+  }
+}
+
+template <int EPI, bool PRE = false>
 __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&r)[32], int row, int row_base, int col0, int M,
                                                       int N, const float* __restrict__ bias,
                                                       const __nv_bfloat16* __restrict__ residual, int64_t ldr,
                                                       __nv_bfloat16* __restrict__ out, int64_t ldo, uint8_t* stage,
-                                                      int lane) {
+                                                      int lane, const ResidualChunk* pre = nullptr) {
   if (col0 >= N) return;  // warp-uniform
   const bool row_ok = row < M;
   const __nv_bfloat16* rrow = (EPI == GEMM_EPI_BIAS_RESIDUAL) ? residual + int64_t(row) * ldr + col0 : nullptr;
@@ -190,6 +205,16 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&r)[32], i
         for (int j = 0; j < 8; j += 2) gelu_erf2(x[j], x[j + 1]);
       }
       if (EPI == GEMM_EPI_BIAS_RESIDUAL) {
+        if constexpr (PRE) {
+          const uint4 rv = pre->v[v];   // zero outside the matrix
+          const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+            x[2 * j] += __bfloat162float(p.x);
+            x[2 * j + 1] += __bfloat162float(p.y);
+          }
+        } else {
         if (row_ok) {
           const uint4 rv = *reinterpret_cast<const uint4*>(rrow + v * 8);
           const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
@@ -199,6 +224,7 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&r)[32], i
             x[2 * j] += __bfloat162float(p.x);
             x[2 * j + 1] += __bfloat162float(p.y);
           }
+        }
         }
       }
       o.x = pack_bf16x2(x[0], x[1]);
@@ -511,16 +537,23 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       } else {
         constexpr int kChunks = kColsPerWarp / 32;
         static_assert(kChunks % 2 == 0, "the pipelined epilogue walks the chunks in pairs");
+        constexpr bool kRes = EPI == GEMM_EPI_BIAS_RESIDUAL;
         uint32_t ra[32], rb[32];
+        ResidualChunk qa, qb;                                      // residual rows travel one chunk ahead as well
         tmem_ld_32x32b_x32(t_addr, ra);
+        if constexpr (kRes) load_residual_chunk(qa, residual, ldr, row, n0, M, N);
 #pragma unroll 1
         for (int c = 0; c < kChunks; c += 2) {
           tmem_ld_wait_regs(ra);                                   // chunk c has landed
           tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, rb);          // chunk c+1 in flight during chunk c's math
-          epilogue_chunk_staged<EPI>(ra, row, row_base, n0 + c * 32, M, N, bias, residual, ldr, out, ldo, stage, lane);
+          if constexpr (kRes) load_residual_chunk(qb, residual, ldr, row, n0 + (c + 1) * 32, M, N);
+          epilogue_chunk_staged<EPI, kRes>(ra, row, row_base, n0 + c * 32, M, N, bias, residual, ldr, out, ldo, stage, lane, &qa);
           tmem_ld_wait_regs(rb);
-          if (c + 2 < kChunks) tmem_ld_32x32b_x32(t_addr + (c + 2) * 32, ra);
-          epilogue_chunk_staged<EPI>(rb, row, row_base, n0 + (c + 1) * 32, M, N, bias, residual, ldr, out, ldo, stage, lane);
+          if (c + 2 < kChunks) {
+            tmem_ld_32x32b_x32(t_addr + (c + 2) * 32, ra);
+            if constexpr (kRes) load_residual_chunk(qa, residual, ldr, row, n0 + (c + 2) * 32, M, N);
+          }
+          epilogue_chunk_staged<EPI, kRes>(rb, row, row_base, n0 + (c + 1) * 32, M, N, bias, residual, ldr, out, ldo, stage, lane, &qb);
         }
       }
       tc_fence_before();
