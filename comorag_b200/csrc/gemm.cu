@@ -12,6 +12,8 @@
 //            tile i's epilogue
 //   warps 2-5  epilogue: tcgen05.ld 32 columns at a time, +bias, optional exact
 //            GELU or residual add, round to bf16, 16-byte global stores
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -604,6 +606,10 @@ static int launch_gemm2_e(int epi, const CUtensorMap& tm_a, const CUtensorMap& t
 int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias, const void* residual,
               int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int epi, cudaStream_t stream, int variant) {
   if (M <= 0) return CRAG_OK;
+  // A/B testing of whole forwards: CRAG_GEMM_VARIANT=<bits> applies a variant word to every GEMM that did not ask for
+  // one (read once; unset = the default dispatch).  Not a tuning knob for production use.
+  static const int env_variant = [] { const char* e = getenv("CRAG_GEMM_VARIANT"); return e ? atoi(e) : 0; }();
+  if (variant == 0) variant = env_variant;
   if (N < 8 || K < 8 || N % 8 != 0 || K % 8 != 0) return fail(CRAG_ERR_INVALID, "gemm: N and K must be positive multiples of 8 (N=%d K=%d)", N, K);
   if (lda % 8 || ldw % 8 || ldo % 8 || (epi == GEMM_EPI_BIAS_RESIDUAL && ldr % 8)) return fail(CRAG_ERR_INVALID, "gemm: leading dimensions must be multiples of 8 elements");
   if (!a || !w || !bias || !out || (epi == GEMM_EPI_BIAS_RESIDUAL && !residual)) return fail(CRAG_ERR_INVALID, "gemm: null pointer");
