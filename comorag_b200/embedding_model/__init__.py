@@ -1,7 +1,7 @@
 """Factory + classes, same names as the reference package (embedding_model/__init__.py:1-17)."""
 import logging
 
-from .base import BaseEmbeddingModel, EmbeddingConfig
+from .base import BaseEmbeddingModel, EmbeddingCache, EmbeddingConfig
 from .BGEEmbedding import BGEEmbeddingModel
 
 logger = logging.getLogger(__name__)

@@ -139,3 +139,42 @@ def make_cache_embed(encode_func, cache_file_name: str, device):
 
 
 _CACHE_LOCKS: Dict[str, threading.Lock] = {}
+
+
+class EmbeddingCache:
+    """Process-wide content -> embedding cache with the reference's classmethod API (base.py:222-260: get / set /
+    contains / clear).  The reference backs it with a `multiprocessing.Manager().dict()` that it never uses from a
+    second process (the class has no caller in the reference tree); here it is a lock-guarded dict, and
+    `share_across_processes()` swaps in a manager dict for callers that do fork workers."""
+
+    _cache: Dict[Any, Any] = {}
+    _manager = None
+    _lock = threading.Lock()
+
+    @classmethod
+    def share_across_processes(cls) -> None:
+        with cls._lock:
+            if cls._manager is None:
+                import multiprocessing
+                cls._manager = multiprocessing.Manager()
+                shared = cls._manager.dict()
+                shared.update(cls._cache)
+                cls._cache = shared
+
+    @classmethod
+    def get(cls, content):
+        return cls._cache.get(content)
+
+    @classmethod
+    def set(cls, content, embedding) -> None:
+        with cls._lock:
+            cls._cache[content] = embedding
+
+    @classmethod
+    def contains(cls, content) -> bool:
+        return content in cls._cache
+
+    @classmethod
+    def clear(cls) -> None:
+        with cls._lock:
+            cls._cache.clear()

@@ -228,3 +228,20 @@ def test_shard_bounds_and_packed_records_properties():
 
     bounds()
     records()
+
+
+def test_embedding_cache_classmethods():
+    """base.py:222-260's EmbeddingCache API (get / set / contains / clear), including from several threads."""
+    import threading
+    from comorag_b200.embedding_model import EmbeddingCache
+    EmbeddingCache.clear()
+    assert EmbeddingCache.get("a") is None and not EmbeddingCache.contains("a")
+    v = np.arange(4, dtype=np.float32)
+    EmbeddingCache.set("a", v)
+    assert EmbeddingCache.contains("a") and np.array_equal(EmbeddingCache.get("a"), v)
+    ts = [threading.Thread(target=lambda i=i: EmbeddingCache.set(f"k{i}", i)) for i in range(16)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert all(EmbeddingCache.get(f"k{i}") == i for i in range(16))
+    EmbeddingCache.clear()
+    assert not EmbeddingCache.contains("a") and not EmbeddingCache.contains("k3")
