@@ -10,6 +10,8 @@ python tools/gpu_check_encoder.py --only gemm > gpurun_out/r2_gemm_cases.log 2>&
 python tools/gpu_check_encoder.py --kind perf --case 0 > gpurun_out/r2_perf_default.log 2>&1
 CRAG_GEMM_VARIANT=4 python tools/gpu_check_encoder.py --kind perf --case 0 > gpurun_out/r2_perf_variant4.log 2>&1
 CRAG_GEMM_VARIANT=4 python tools/gpu_check_encoder.py --kind enc --case 4 > gpurun_out/r2_enc_variant4.log 2>&1
+CRAG_GEMM_VARIANT=12 python tools/gpu_check_encoder.py --kind perf --case 0 > gpurun_out/r2_perf_variant12.log 2>&1
+CRAG_GEMM_VARIANT=12 python tools/gpu_check_encoder.py --kind enc --case 4 > gpurun_out/r2_enc_variant12.log 2>&1
 # 2b. attention SPLIT variant (8 softmax warps, two threads per query row): correctness + timing, then whole forward
 CRAG_ATTN_VARIANT=1 python tools/gpu_check_encoder.py --only attn > gpurun_out/r2_attn_split_cases.log 2>&1
 python tools/gpu_check_encoder.py --only attn > gpurun_out/r2_attn_default_cases.log 2>&1
@@ -21,4 +23,4 @@ timeout 600 python tools/ivf_bench.py > gpurun_out/r2_ivf_12m.json 2> gpurun_out
 timeout 300 python tools/ivf_bench.py --rows 2000000 --nlist 1024 --nprobe 16 > gpurun_out/r2_ivf_2m.json 2> gpurun_out/r2_ivf_2m.err
 # 4. config-5 cycle
 timeout 300 python tools/loop_bench.py > gpurun_out/r2_loop.json 2> gpurun_out/r2_loop.err
-tail -3 gpurun_out/r2_pytest.log; grep -h '"variant": 4' gpurun_out/r2_gemm_cases.log; grep -h '"tc": 1' gpurun_out/r2_attn_split_cases.log gpurun_out/r2_attn_default_cases.log; cat gpurun_out/r2_perf_*.log gpurun_out/r2_enc_*.log gpurun_out/r2_ivf_*.json gpurun_out/r2_loop.json
+tail -3 gpurun_out/r2_pytest.log; grep -hE '"variant": (4|8|12)' gpurun_out/r2_gemm_cases.log; grep -h '"tc": 1' gpurun_out/r2_attn_split_cases.log gpurun_out/r2_attn_default_cases.log; cat gpurun_out/r2_perf_*.log gpurun_out/r2_enc_*.log gpurun_out/r2_ivf_*.json gpurun_out/r2_loop.json
