@@ -625,11 +625,14 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const floa
     // CTA-pair kernel: each CTA fetches half of the W tile
     rc = make_tmap_bf16_2d(&tm_b, w, uint64_t(N), uint64_t(K), uint64_t(ldw) * 2, wide ? 128 : 64);
     if (rc != CRAG_OK) return rc;
-    if ((variant & 8) && wide && epi == GEMM_EPI_BIAS_GELU) {
-      // A/B switch (unvalidated): 16 epilogue warps (four per TMEM lane quadrant, 64 columns each) for the
-      // issue-bound GELU epilogue; one pipeline stage is traded for their staging tiles
-      if (variant & 4) return launch_gemm2_t<256, 5, GEMM_EPI_BIAS_GELU, 16, true>(tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
-      return launch_gemm2_t<256, 5, GEMM_EPI_BIAS_GELU, 16, false>(tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
+    if ((variant & 8) && wide && epi != GEMM_EPI_BIAS) {
+      // A/B switch (unvalidated): 16 epilogue warps (four per TMEM lane quadrant, 64 columns each) for the GELU
+      // (issue-bound) and residual (load-latency-bound) epilogues; one pipeline stage is traded for their staging tiles
+      if (epi == GEMM_EPI_BIAS_GELU) {
+        if (variant & 4) return launch_gemm2_t<256, 5, GEMM_EPI_BIAS_GELU, 16, true>(tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
+        return launch_gemm2_t<256, 5, GEMM_EPI_BIAS_GELU, 16, false>(tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
+      }
+      return launch_gemm2_t<256, 5, GEMM_EPI_BIAS_RESIDUAL, 16, false>(tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
     }
     if (variant & 4) {  // A/B switch: pipelined TMEM reads in the epilogue
       if (wide) return launch_gemm2_e<256, 6, true>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
@@ -651,7 +654,7 @@ extern "C" int crag_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t
                               int epilogue, crag_stream_t stream) {
   // bits 8+ of `epilogue` select a kernel variant for A/B testing: 0 = default dispatch, bit 0 = force single-CTA,
   // bit 1 = force the BN = 128 tile, bit 2 = pipelined TMEM reads in the CTA-pair epilogue (unvalidated),
-  // bit 3 = 16 epilogue warps for the GELU epilogue (unvalidated)
+  // bit 3 = 16 epilogue warps for the GELU / residual epilogues (unvalidated)
   return crag::gemm_bf16(a, lda, w, ldw, bias, residual, ldr, out, ldo, m, n, k, epilogue & 0xFF,
                          static_cast<cudaStream_t>(stream), epilogue >> 8);
 }

@@ -26,6 +26,7 @@ GEMM_CASES = [  # M, N, K, epi, variant (0 = default dispatch: CTA-pair kernel w
     (16384, 3072, 1024, 0, 4), (16384, 1024, 1024, 2, 4), (16384, 4096, 1024, 1, 4), (16384, 1024, 4096, 2, 4),
     # bit 3 = 16 epilogue warps for the GELU epilogue (wide tiles only), alone and with the pipelined reads
     (1000, 1024, 384, 1, 8), (16384, 4096, 1024, 1, 8), (16384, 4096, 1024, 1, 12), (777, 1536, 384, 1, 12),
+    (512, 1024, 1536, 2, 8), (16384, 1024, 1024, 2, 8), (16384, 1024, 4096, 2, 8),
 ]
 ATTN_CASES = [  # H, heads, lengths, tc (1 = tcgen05 kernel)
     (128, 4, [5, 64, 65, 1, 130], 0), (1024, 16, [512, 33, 200, 512], 0), (384, 12, [77, 512, 300], 0), (768, 12, [128] * 6, 0),
