@@ -8,12 +8,14 @@ F.normalize.  Weight names follow HF's BertModel state dict.
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import json
 import os
 import threading
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import _native
@@ -219,15 +221,8 @@ class BertEncoderB200:
         """List of token-id lists (already with [CLS]/[SEP]) -> fp32 [n, H] on the device."""
         if len(seqs) == 0:
             return torch.empty((0, self.config.hidden_size), dtype=torch.float32, device=self.device)
-        lens = [len(s) for s in seqs]
-        if min(lens) < 1:
-            raise ValueError("empty token sequence")
-        flat = torch.tensor([t for s in seqs for t in s], dtype=torch.int32).pin_memory()
-        cu = torch.zeros(len(seqs) + 1, dtype=torch.int32)
-        cu[1:] = torch.tensor(lens, dtype=torch.int32).cumsum(0)
-        cu = cu.pin_memory()
-        return self.forward_packed(flat.to(self.device, non_blocking=True), cu.to(self.device, non_blocking=True),
-                                   max(lens), normalize)
+        flat, cu, longest = _pack(seqs, self.device)
+        return self.forward_packed(flat, cu, longest, normalize)
 
     # ------------------------------------------------- cross-encoder scoring
     def classify_packed(self, token_ids: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int,
@@ -256,14 +251,22 @@ class BertEncoderB200:
         return self.classify_packed(flat, cu, longest)
 
 
-def _pack(seqs: Sequence[Sequence[int]], device: torch.device):
-    lens = [len(s) for s in seqs]
-    if min(lens) < 1:
+def _flatten(seqs: Sequence[Sequence[int]]):
+    """Token-id lists -> (flat int32 [T], cu_seqlens int32 [n + 1], longest) as numpy, without a Python-level pass
+    over the tokens (the per-token list comprehension cost ~1 ms per 16k tokens, 5-8 % of an encode step)."""
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
+    if lens.size == 0 or int(lens.min()) < 1:
         raise ValueError("empty token sequence")
-    flat = torch.tensor([t for s in seqs for t in s], dtype=torch.int32).pin_memory()
-    cu = torch.zeros(len(seqs) + 1, dtype=torch.int32)
-    cu[1:] = torch.tensor(lens, dtype=torch.int32).cumsum(0)
-    return flat.to(device, non_blocking=True), cu.pin_memory().to(device, non_blocking=True), max(lens)
+    flat = np.fromiter(itertools.chain.from_iterable(seqs), dtype=np.int32, count=int(lens.sum()))
+    cu = np.zeros(len(seqs) + 1, dtype=np.int32)
+    np.cumsum(lens, out=cu[1:])
+    return flat, cu, int(lens.max())
+
+
+def _pack(seqs: Sequence[Sequence[int]], device: torch.device):
+    flat, cu, longest = _flatten(seqs)
+    return (torch.from_numpy(flat).pin_memory().to(device, non_blocking=True),
+            torch.from_numpy(cu).pin_memory().to(device, non_blocking=True), longest)
 
 
 def random_head_state_dict(cfg: EncoderConfig, n_labels: int = 1, seed: int = 0, std: float = 0.02, device="cpu"):

@@ -245,3 +245,18 @@ def test_embedding_cache_classmethods():
     assert all(EmbeddingCache.get(f"k{i}") == i for i in range(16))
     EmbeddingCache.clear()
     assert not EmbeddingCache.contains("a") and not EmbeddingCache.contains("k3")
+
+
+def test_token_flattening_matches_the_plain_loops():
+    from comorag_b200.encoder import _flatten
+    rng = np.random.default_rng(1)
+    seqs = [rng.integers(0, 250002, int(n)).tolist() for n in (1, 512, 37, 2, 300)]
+    seqs[2] = tuple(seqs[2])                                           # any sequence type
+    flat, cu, longest = _flatten(seqs)
+    assert flat.dtype == np.int32 and cu.dtype == np.int32 and longest == 512
+    np.testing.assert_array_equal(flat, np.array([t for s in seqs for t in s], dtype=np.int32))
+    np.testing.assert_array_equal(cu, np.concatenate([[0], np.cumsum([len(s) for s in seqs])]))
+    with pytest.raises(ValueError):
+        _flatten([[1, 2], []])
+    with pytest.raises(ValueError):
+        _flatten([])
