@@ -161,3 +161,25 @@ def test_parquet_is_written_in_row_batches(gold, tmp_path, monkeypatch):
     again = EmbeddingStore(model, str(tmp_path / "e"), 4, "chunk")
     assert again.get_all_ids() == gold["hash_ids"]
     np.testing.assert_array_equal(again.get_embeddings(again.hash_ids), gold["embeddings"])
+
+
+def test_reads_the_parquet_the_reference_wrote(gold, tmp_path):
+    """tests/golden/vdb_chunk_reference.parquet was written by the REFERENCE's EmbeddingStore (pandas -> pyarrow,
+    embedding_store.py:109-120; generator: tests/golden/make_golden_parquet.py).  Our store must load it as-is; the
+    opposite direction (the reference loading our file) was checked where the reference can run and is recorded in
+    tests/golden/parquet_interop.json."""
+    import shutil
+    d = tmp_path / "chunk_embeddings"
+    d.mkdir()
+    shutil.copy(os.path.join(HERE, "golden", "vdb_chunk_reference.parquet"), d / "vdb_chunk.parquet")
+    model = ReplayModel(gold)
+    store = EmbeddingStore(model, str(d), 4, "chunk")
+    assert store.get_all_ids() == gold["hash_ids"] and store.texts == gold["texts"]
+    np.testing.assert_array_equal(store.get_embeddings(store.hash_ids), gold["embeddings"])
+    assert store.insert_strings(gold["texts"][:3]) == {} and model.calls == []        # nothing re-encoded
+    store.insert_strings(["one more chunk"]) if "one more chunk" in model.table else None
+    interop = json.load(open(os.path.join(HERE, "golden", "parquet_interop.json")))
+    assert all(v is True for k, v in interop["reference_read_ours"].items() if isinstance(v, bool))
+    import pyarrow.parquet as pq
+    ref_schema = pq.read_schema(os.path.join(HERE, "golden", "vdb_chunk_reference.parquet"))
+    assert {n: str(ref_schema.field(n).type) for n in ref_schema.names} == gold["parquet_schema"]
