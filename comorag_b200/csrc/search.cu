@@ -68,15 +68,24 @@ struct IvfArgs {
   const float* coarse;
 };
 struct NoIvfArgs {};
-template <bool IVF> struct IvfParam { using type = NoIvfArgs; };
-template <> struct IvfParam<true> { using type = IvfArgs; };
+// Score-all variant (SCORES = true): the full-array contracts of the reference -- get_fact_scores returns the score
+// of EVERY fact row (ComoRAG.py:937-948) and dense_passage_retrieval a permutation of ALL rows (:950-967, consumed
+// rank by rank by PPR at :1034-1042).  Same TMA -> tcgen05 -> TMEM stream; the select warps write the fp32 scores
+// (out[q * ld + row], one coalesced 128-byte store per warp and query) instead of running the selector.
+struct ScoreArgs {
+  float* out;
+  int64_t ld;
+};
+template <bool IVF, bool SCORES> struct IvfParam { using type = NoIvfArgs; };
+template <> struct IvfParam<true, false> { using type = IvfArgs; };
+template <> struct IvfParam<false, true> { using type = ScoreArgs; };
 
-template <int KLIST, int CAP, int STAGES, bool IVF = false>
+template <int KLIST, int CAP, int STAGES, bool IVF = false, bool SCORES = false>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_constant__ CUtensorMap tm_q,
                    int n_rows, int num_kb, int nq, int k, const uint64_t* __restrict__ after_keys,
                    const float* __restrict__ thr_floor, int floor_stride, uint64_t* __restrict__ part_keys,
-                   float* __restrict__ part_minmax, const typename IvfParam<IVF>::type ivf) {
+                   float* __restrict__ part_minmax, const typename IvfParam<IVF, SCORES>::type ivf) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -218,6 +227,19 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       if (lane == 0) mbar_arrive(&bar_tempty[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
 
+      if constexpr (SCORES) {
+        const int srow = tile * kTileRows + quad * 32 + lane;
+        if (srow < n_rows) {
+#pragma unroll
+          for (int q = 0; q < kNQ; ++q) {
+            const float s = __uint_as_float(r[q]);
+            mn[q] = fminf(mn[q], s);
+            mx[q] = fmaxf(mx[q], s);
+            if (q < nq) ivf.out[int64_t(q) * ivf.ld + srow] = s;
+          }
+        }
+        continue;
+      }
       int row;
       uint32_t pending = 0;
       if constexpr (!IVF) {
@@ -311,12 +333,14 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
 
     // drain candidate buffers, then publish this CTA's lists and (min, max)
     named_bar_sync(1, kEpiThreads);
-    for (int q = ew; q < kNQ; q += 4) {
-      const int c = min(cnt[q], CAP);
-      if (c > 0) flush_query<KLIST, CAP>(keys + q * L::kKeysPerQuery, c, k, &thr_key[q], lane);
-      __syncwarp();
-      uint64_t* dst = part_keys + (size_t(blockIdx.x) * kNQ + q) * k;
-      for (int j = lane; j < k; j += 32) dst[j] = keys[q * L::kKeysPerQuery + j];
+    if constexpr (!SCORES) {
+      for (int q = ew; q < kNQ; q += 4) {
+        const int c = min(cnt[q], CAP);
+        if (c > 0) flush_query<KLIST, CAP>(keys + q * L::kKeysPerQuery, c, k, &thr_key[q], lane);
+        __syncwarp();
+        uint64_t* dst = part_keys + (size_t(blockIdx.x) * kNQ + q) * k;
+        for (int j = lane; j < k; j += 32) dst[j] = keys[q * L::kKeysPerQuery + j];
+      }
     }
 #pragma unroll
     for (int q = 0; q < kNQ; ++q) {
@@ -834,4 +858,71 @@ extern "C" int crag_merge_topk_packed(const void* records, int64_t record_bytes,
   return crag::merge_pairs(reinterpret_cast<const float*>(base + a), reinterpret_cast<const int64_t*>(base),
                            reinterpret_cast<const float*>(base + b), record_bytes, record_bytes, record_bytes, parts, nq, k,
                            out_ids, out_scores, out_minmax, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------ score-all pass
+namespace crag {
+namespace {
+// (min, max) over the per-CTA partials of a score-all pass: one warp per query.
+__global__ void minmax_reduce_kernel(const float* __restrict__ part_minmax, int parts, int nq, float* __restrict__ out) {
+  const int q = blockIdx.x, lane = threadIdx.x;
+  if (q >= nq) return;
+  float a = INFINITY, b = -INFINITY;
+  for (int p = lane; p < parts; p += 32) {
+    a = fminf(a, part_minmax[(size_t(p) * kNQ + q) * 2 + 0]);
+    b = fmaxf(b, part_minmax[(size_t(p) * kNQ + q) * 2 + 1]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+  }
+  if (lane == 0) {
+    out[size_t(q) * 2 + 0] = a;
+    out[size_t(q) * 2 + 1] = b;
+  }
+}
+}  // namespace
+}  // namespace crag
+
+extern "C" int crag_search_scores(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride,
+                                  const void* queries, int nq, float* out_scores, int64_t out_ld, float* out_minmax,
+                                  void* workspace, size_t workspace_bytes, crag_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const SearchPlan plan = plan_search(1);
+  int rc = check_search_args(corpus, n_rows, dim, corpus_row_stride, queries, nq, 1, workspace, workspace_bytes, plan);
+  if (rc != CRAG_OK) return rc;
+  if (!out_scores || out_ld < n_rows) return fail(CRAG_ERR_INVALID, "crag_search_scores: need out_scores and out_ld >= n_rows");
+  const int grid = scan_grid(n_rows, plan);
+  if (grid == 0) {
+    if (out_minmax) {   // empty shard: (+inf, -inf), as crag_search_topk
+      minmax_reduce_kernel<<<nq, 32, 0, stream>>>(nullptr, 0, nq, out_minmax);
+      CRAG_CUDA_OK(cudaGetLastError());
+    }
+    return CRAG_OK;
+  }
+  float* part_minmax = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes);
+  CUtensorMap tm_corpus;
+  rc = make_tmap_bf16_2d(&tm_corpus, corpus, uint64_t(n_rows), uint64_t(dim), uint64_t(corpus_row_stride) * 2, kTileRows);
+  if (rc != CRAG_OK) return rc;
+  const int num_kb = dim / kBlockK;
+  using L = SearchLayout<16, 16, 9>;
+  auto kern = search_topk_kernel<16, 16, 9, false, true>;
+  const size_t smem = L::smem_bytes(num_kb);
+  CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  for (int q0 = 0; q0 < nq; q0 += kNQ) {
+    const int nqc = (nq - q0) < kNQ ? (nq - q0) : kNQ;
+    CUtensorMap tm_q;
+    rc = make_tmap_bf16_2d(&tm_q, static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2, uint64_t(nqc), uint64_t(dim), uint64_t(dim) * 2, kNQ);
+    if (rc != CRAG_OK) return rc;
+    ScoreArgs sa{out_scores + int64_t(q0) * out_ld, out_ld};
+    kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, int(n_rows), num_kb, nqc, 1, nullptr, nullptr, 0, nullptr,
+                                                 part_minmax, sa);
+    CRAG_CUDA_OK(cudaGetLastError());
+    if (out_minmax) {
+      minmax_reduce_kernel<<<nqc, 32, 0, stream>>>(part_minmax, grid, nqc, out_minmax + size_t(q0) * 2);
+      CRAG_CUDA_OK(cudaGetLastError());
+    }
+  }
+  return CRAG_OK;
 }

@@ -39,6 +39,11 @@ def mean_pooling(token_embeddings: torch.Tensor, mask: torch.Tensor) -> torch.Te
 
 
 class BGEEmbeddingModel(BaseEmbeddingModel):
+    # batch_encode overwrites any caller instruction with the passage instruction (BGEEmbedding.py:150-155), so the
+    # reference's "query_to_fact" and "query_to_passage" encodes of one text are the same row; callers may rely on it
+    instruction_is_forced = True
+    _MEMO_ROWS = 512      # single-text batch_encode results kept (one tri_retrieve asks for the same query 4 times)
+
     def __init__(self, global_config: Optional[Any] = None, embedding_model_name: Optional[str] = None,
                  encoder: Optional[BertEncoderB200] = None, tokenizer: Optional[Any] = None) -> None:
         super().__init__(global_config=global_config)
@@ -58,6 +63,8 @@ class BGEEmbeddingModel(BaseEmbeddingModel):
         self.embedding_dim = self.embedding_model.config.hidden_size
         self._token_budget = int(cfg_get(self.global_config, "embedding_token_budget", 16384))
         self._tok_lock = threading.Lock()  # HF fast tokenizers are not re-entrant across threads
+        self._memo = {}                    # (text, max_length, normalize) -> np.float32 [1, D]
+        self._memo_lock = threading.Lock()
         # optional dynamic batching of concurrent callers (ComoRAG.py:436-441 runs <=16 threads); off by default
         self._coalescer = None
         if cfg_get(self.global_config, "embedding_coalesce", False):
@@ -140,6 +147,15 @@ class BGEEmbeddingModel(BaseEmbeddingModel):
         else:
             params["instruction"] = params.get("passage_instruction", _INSTRUCTION)
         batch_size = params.pop("batch_size", 16)
+        # One tri_retrieve encodes the same query string up to four times (ComoRAG.py:941,953 twice, and
+        # embed_utils.py:143); the forward is deterministic, so a repeated single text is served from a small memo.
+        memo_key = None
+        if len(texts) == 1 and isinstance(texts[0], str):
+            memo_key = (texts[0], params.get("max_length"), bool(kwargs.get("normalize", True)))
+            with self._memo_lock:
+                hit = self._memo.get(memo_key)
+            if hit is not None:
+                return hit.copy()
         if len(texts) <= batch_size:
             params["prompts"] = texts
             results = self.encode(**params)
@@ -153,7 +169,13 @@ class BGEEmbeddingModel(BaseEmbeddingModel):
             results = results.detach().float().cpu().numpy()
         if self.embedding_config.norm and not kwargs.get("normalize", True):
             results = (results.T / np.linalg.norm(results, axis=1)).T
-        return np.ascontiguousarray(results, dtype=np.float32)
+        results = np.ascontiguousarray(results, dtype=np.float32)
+        if memo_key is not None:
+            with self._memo_lock:
+                if len(self._memo) >= self._MEMO_ROWS:
+                    self._memo.pop(next(iter(self._memo)))
+                self._memo[memo_key] = results.copy()
+        return results
 
     def encode_queries(self, queries: Union[str, List[str]], **kwargs) -> np.ndarray:
         kwargs["is_query"] = True

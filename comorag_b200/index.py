@@ -204,6 +204,56 @@ class DenseIndex:
                     after = last
         return ids, scores, minmax
 
+    # ------------------------------------------------- full-array contracts
+    def scores_device(self, queries: torch.Tensor, stream: Optional[torch.cuda.Stream] = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Raw inner products of EVERY row for a device bf16 [nq, dim_pad] query block (crag_search_scores): the
+        np.dot(E, q.T) of ComoRAG.py:944 / :958-960 when a caller needs the whole array.  Returns (scores fp32
+        [nq, n_rows], minmax fp32 [nq, 2]) on the device."""
+        if queries.dtype != torch.bfloat16 or queries.dim() != 2 or queries.shape[1] != self.dim_pad:
+            raise ValueError(f"queries must be bf16 [nq, {self.dim_pad}]")
+        queries = queries.contiguous()
+        nq = queries.shape[0]
+        lib = _native.load()
+        dev = self.device
+        buf, n_rows = self._snapshot()
+        with torch.cuda.device(dev):
+            st = stream if stream is not None else torch.cuda.current_stream(dev)
+            with torch.cuda.stream(st):
+                ld = max(n_rows, 1)
+                scores = torch.empty((nq, ld), dtype=torch.float32, device=dev)
+                minmax = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+                ws_bytes = lib.crag_search_workspace_bytes(nq, 1)
+                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+                rc = lib.crag_search_scores(buf.data_ptr() if n_rows else 0, n_rows, self.dim_pad,
+                                            buf.stride(0) if buf.shape[0] else self.dim_pad, queries.data_ptr(), nq,
+                                            scores.data_ptr(), ld, minmax.data_ptr(), ws.data_ptr(), ws_bytes,
+                                            st.cuda_stream)
+                _native.check(rc, "crag_search_scores")
+        return scores[:, :n_rows], minmax
+
+    def rank_device(self, scores_row: torch.Tensor, stream: Optional[torch.cuda.Stream] = None
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Full descending ranking of one fp32 score row on the device (crag_rank_scores; ties by ascending row):
+        np.argsort(scores)[::-1] + the gather of ComoRAG.py:965-966.  Returns (ids int64 [n], scores fp32 [n])."""
+        if scores_row.dtype != torch.float32 or scores_row.dim() != 1 or not scores_row.is_contiguous():
+            raise ValueError("scores_row must be a contiguous fp32 vector")
+        n = scores_row.shape[0]
+        lib = _native.load()
+        dev = self.device
+        with torch.cuda.device(dev):
+            st = stream if stream is not None else torch.cuda.current_stream(dev)
+            with torch.cuda.stream(st):
+                ids = torch.empty((n,), dtype=torch.int64, device=dev)
+                out = torch.empty((n,), dtype=torch.float32, device=dev)
+                if n:
+                    ws_bytes = lib.crag_rank_workspace_bytes(n)
+                    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+                    rc = lib.crag_rank_scores(scores_row.data_ptr(), n, ids.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                              ws_bytes, st.cuda_stream)
+                    _native.check(rc, "crag_rank_scores")
+        return ids, out
+
     def prepare_queries(self, queries) -> torch.Tensor:
         """Host/device float [nq, dim] -> device bf16 [nq, dim_pad]."""
         q = torch.as_tensor(queries)

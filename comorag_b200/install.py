@@ -4,9 +4,13 @@
     crag.install("src.comorag")          # before or after `from src.comorag import ComoRAG`
     rag = ComoRAG(global_config=BaseConfig(embedding_model_name=".../bge-large-en-v1.5", ...))
 
-`ComoRAG.py` binds `_get_embedding_model_class`, `EmbeddingStore`, `DSPyFilter`, `get_similar_summaries` by
-`from ... import` (ComoRAG.py:21-35), so the substitution rewrites those names in every already-imported module of the
-package as well as in their defining modules; class bodies resolve them from module globals at call time.
+`ComoRAG.py` binds `_get_embedding_model_class`, `EmbeddingStore`, `DSPyFilter`, `get_similar_summaries`,
+`retrieve_knn` by `from ... import` (ComoRAG.py:21-35), so the substitution rewrites those names in every
+already-imported module of the package as well as in their defining modules; class bodies resolve them from module
+globals at call time.  The search half of the path lives in METHODS of the `ComoRAG` class itself
+(`prepare_retrieval_objects`, `get_query_embeddings`, `get_fact_scores`, `dense_passage_retrieval`,
+ComoRAG.py:876-967): those are replaced on the class object (comorag_b200/comorag_methods.py), the file stays
+untouched.
 """
 from __future__ import annotations
 
@@ -15,9 +19,11 @@ import sys
 from typing import Dict
 
 
-def install(package: str = "src.comorag", rerank: bool = False, summaries: bool = True) -> Dict[str, int]:
-    """Returns {name: number of module attributes rebound}.  `rerank=True` also swaps the LLM filter for the
-    dense reranker (new arithmetic, off by default so answers stay reference-identical)."""
+def install(package: str = "src.comorag", rerank: bool = False, summaries: bool = True, search: bool = True,
+            knn: bool = True) -> Dict[str, int]:
+    """Returns {name: number of module attributes (or class methods) rebound}.  `rerank=True` also swaps the LLM
+    filter for the dense reranker (new arithmetic, off by default so answers stay reference-identical); `search`
+    rebinds the four ComoRAG retrieval methods, `knn` the synonymy-edge retrieve_knn."""
     from . import embedding_model as em
     from . import embedding_store as es
     from . import rerank as rr
@@ -33,6 +39,9 @@ def install(package: str = "src.comorag", rerank: bool = False, summaries: bool 
     if summaries:
         ref_eu = importlib.import_module(package + ".utils.embed_utils")
         swaps["get_similar_summaries"] = (ref_eu.get_similar_summaries, rt.get_similar_summaries)
+    if knn:
+        ref_eu = importlib.import_module(package + ".utils.embed_utils")
+        swaps["retrieve_knn"] = (ref_eu.retrieve_knn, rt.retrieve_knn)
     if rerank:
         ref_rr = importlib.import_module(package + ".rerank")
         swaps["DSPyFilter"] = (ref_rr.DSPyFilter, rr.DSPyFilter)
@@ -44,4 +53,27 @@ def install(package: str = "src.comorag", rerank: bool = False, summaries: bool 
             if getattr(mod, attr, None) is old:
                 setattr(mod, attr, new)
                 counts[attr] += 1
+    if search:
+        from . import comorag_methods as cm
+        main = sys.modules.get(package + ".ComoRAG") or importlib.import_module(package + ".ComoRAG")
+        cls = main.ComoRAG
+        originals = cls.__dict__.get("_comorag_b200_originals")
+        if originals is None:
+            originals = {name: cls.__dict__[name] for name in cm.METHODS}
+            cls._comorag_b200_originals = originals       # uninstall() / the parity tests can reach the reference methods
+        for name, fn in cm.METHODS.items():
+            setattr(cls, name, fn)
+            counts["ComoRAG." + name] = 1
     return counts
+
+
+def uninstall_search(package: str = "src.comorag") -> None:
+    """Put the reference's own retrieval methods back on the ComoRAG class (used by the parity tests to run the
+    reference arm in the same process)."""
+    main = sys.modules.get(package + ".ComoRAG")
+    if main is None:
+        return
+    originals = main.ComoRAG.__dict__.get("_comorag_b200_originals")
+    if originals:
+        for name, fn in originals.items():
+            setattr(main.ComoRAG, name, fn)

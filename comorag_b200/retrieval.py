@@ -13,8 +13,6 @@ import numpy as np
 
 from .index import DenseIndex, MAX_K
 
-FULL_RANKING_PAGED_MAX = 32768   # up to this many rows a full permutation is served by rank-continuation passes
-
 
 def min_max_normalize(x: np.ndarray) -> np.ndarray:
     """misc_utils.py:141-150."""
@@ -45,39 +43,28 @@ def dense_topk(index: DenseIndex, query_embeddings, k: int) -> Tuple[np.ndarray,
 def dense_passage_retrieval(index: DenseIndex, query_embedding, top_k: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
     """ComoRAG.py:950-967 for one query embedding [1, D] or [D].
 
-    top_k=None keeps the reference contract (a permutation of ALL rows + all normalised scores): up to
-    FULL_RANKING_PAGED_MAX rows it is produced by the fused kernel alone (rank continuation, 128 ranks per pass);
-    beyond that all N scores are computed and sorted on the device.  With top_k only the first top_k ranks are
-    produced (what tri_retrieve actually consumes, ComoRAG.py:499,516).
+    top_k=None keeps the reference contract (a permutation of ALL rows + all min-max-normalised scores, consumed rank
+    by rank by PPR at ComoRAG.py:1034-1042): one score-all pass of the search kernel (crag_search_scores) and the
+    device radix sort (crag_rank_scores), whatever the shard size; only the int64 permutation and the fp32 scores
+    come back to the host.  With top_k only the first top_k ranks are produced by the fused top-k kernel (what
+    tri_retrieve consumes at ComoRAG.py:499,516).
     """
-    import torch
     if top_k is not None:
         ids, sc = dense_topk(index, query_embedding, top_k)
         return ids[0], sc[0]
-    n = index.n_rows
-    if n <= FULL_RANKING_PAGED_MAX:
-        # exact full ranking with the fused kernel alone: ceil(N/128) rank-continuation passes (ComoRAG-scale
-        # corpora have 1e3-1e4 passages; each pass over such a shard is a few tens of microseconds)
-        ids, scores, minmax = index.search(query_embedding, max(n, 1))
-        valid = ids[0] >= 0
-        return ids[0][valid], normalize_topk_scores(scores, minmax)[0][valid]
-    # big shards: all N scores in one device pass, sorted on the device (a permutation of 1e6+ rows is not a top-k)
     q = index.prepare_queries(query_embedding)
-    scores = (index.matrix().float() @ q[0, : index.dim].float())  # [N] fp32 on device
-    mn, mx = scores.min(), scores.max()
-    norm = torch.ones_like(scores) if float(mx - mn) == 0.0 else (scores - mn) / (mx - mn)
-    order = torch.argsort(norm, descending=True, stable=True)
-    return order.cpu().numpy(), norm[order].cpu().numpy()
+    scores, minmax = index.scores_device(q[:1])
+    order, sorted_scores = index.rank_device(scores[0].contiguous())
+    return order.cpu().numpy(), normalize_topk_scores(sorted_scores.cpu().numpy()[None, :], minmax.cpu().numpy())[0]
 
 
 def get_fact_scores(index: DenseIndex, query_embedding) -> np.ndarray:
     """ComoRAG.py:937-948: min-max-normalised score of EVERY fact row, in row order (callers slice it with
-    np.argsort(...)[-k:][::-1], ComoRAG.py:475 / :1073 -- prefer get_fact_scores_topk for that).  Built from the
-    exact full ranking (rank continuation for ComoRAG-scale fact tables, device pass beyond that)."""
-    order, sorted_scores = dense_passage_retrieval(index, query_embedding)
-    out = np.empty(index.n_rows, dtype=np.float32)
-    out[order] = sorted_scores
-    return out
+    np.argsort(...)[-k:][::-1] and index it by fact row, ComoRAG.py:475 / :1054 / :1073).  One score-all pass of
+    the search kernel; the affine rescale is the reference's own expression applied to the returned scores."""
+    q = index.prepare_queries(query_embedding)
+    scores, minmax = index.scores_device(q[:1])
+    return normalize_topk_scores(scores.cpu().numpy(), minmax.cpu().numpy())[0]
 
 
 def get_fact_scores_topk(index: DenseIndex, query_embedding, link_top_k: int) -> Tuple[np.ndarray, np.ndarray]:

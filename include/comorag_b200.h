@@ -128,6 +128,28 @@ CRAG_API int crag_merge_topk(const float* scores, const int64_t* ids, const floa
 CRAG_API int crag_merge_topk_packed(const void* records, int64_t record_bytes, int parts, int nq, int k,
                                     int64_t* out_ids, float* out_scores, float* out_minmax, crag_stream_t stream);
 
+/* Score-all pass: raw inner products of EVERY shard row, for the reference's full-array contracts --
+ *     query_fact_scores = np.dot(self.fact_embeddings, q.T)            (ComoRAG.py:944; get_fact_scores returns all
+ *                                                                      N_f scores and callers index them, :475,:1054)
+ *     query_doc_scores  = np.dot(self.passage_embeddings, q.T)         (ComoRAG.py:958-960)
+ * The same TMA -> tcgen05 stream as crag_search_topk, but the select warps store the fp32 scores instead of
+ * running the top-k selector.  out_scores device fp32, query q's row r at out_scores[q * out_ld + r]
+ * (out_ld >= n_rows); out_minmax device fp32 [nq, 2] or NULL.  Other arguments and the workspace as
+ * crag_search_topk (crag_search_workspace_bytes(nq, 1) bytes suffice). */
+CRAG_API int crag_search_scores(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride,
+                                const void* queries, int nq, float* out_scores, int64_t out_ld, float* out_minmax,
+                                void* workspace, size_t workspace_bytes, crag_stream_t stream);
+
+/* Full descending ranking of one score array on the device:
+ *     sorted_doc_ids = np.argsort(query_doc_scores)[::-1]; sorted_doc_scores = query_doc_scores[sorted_doc_ids]
+ * (ComoRAG.py:965-966; the whole permutation feeds the PPR reset weights, :1034-1042).  Stable LSD radix sort of
+ * (score, row): equal scores keep ascending row order.  scores device fp32 [n] (typically one row of
+ * crag_search_scores); out_ids device int64 [n]; out_scores device fp32 [n]; workspace >=
+ * crag_rank_workspace_bytes(n) bytes, 256-B aligned; n < 2^31. */
+CRAG_API size_t crag_rank_workspace_bytes(int64_t n);
+CRAG_API int crag_rank_scores(const float* scores, int64_t n, int64_t* out_ids, float* out_scores, void* workspace,
+                              size_t workspace_bytes, crag_stream_t stream);
+
 /* ------------------------------------------------------------------ encoder
  * Dense projection of the encoder forward (BGEEmbedding.py:120 runs it through
  * HF's BertModel: attention.self.{query,key,value}, attention.output.dense,
