@@ -29,11 +29,8 @@ constexpr int kAttTileBytes = 128 * 64 * 2;   // 16 KB: Q tile, one P buffer
 constexpr int kAttKVBytes = kAttBN * 64 * 2;  // 8 KB: one K or V block
 // smem: Q 16K | K 2x8K | V 2x8K | P 2x16K | barriers  (~81 KB: two CTAs per SM)
 constexpr size_t kAttSmemBytes = 1024 + kAttTileBytes + 4 * kAttKVBytes + 2 * kAttTileBytes + 256;
-// SPLIT variant (A/B, not dispatched by default, NOT yet validated on hardware): 8 softmax warps, two threads per
-// query row (each owns 32 of the block's 64 keys and 32 of O's 64 columns), so twice as many warps hide the
-// tcgen05.ld / MUFU / barrier latencies the 4-warp version exposes (ncu: 18 % warps active, xu pipe 43 %).
-constexpr int kAttThreadsSplit = 64 + 256;
-constexpr size_t kAttSmemBytesSplit = kAttSmemBytes + 1024;   // + the two half-row sums of every query row
+// (A "split" variant -- 8 softmax warps, two threads per query row -- was measured in round 2: 83.5 us against 79.2 us
+// for this kernel on 32 x 512 tokens x 16 heads; removed.)
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -70,8 +67,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_bmn(uint32_t M, uint3
   return umma_idesc_bf16_f32(M, N) | (1u << 16);  // b_major = MN
 }
 
-template <bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? kAttThreadsSplit : kAttThreads, 2)
+__global__ void __launch_bounds__(kAttThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                     const int32_t* __restrict__ cu_seqlens, int H, float scale_log2e, __nv_bfloat16* __restrict__ ctx) {
   const int seq = blockIdx.z, head = blockIdx.y;
@@ -109,8 +105,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_init(&bar_v_full[s], 1);
       mbar_init(&bar_v_empty[s], 1);
       mbar_init(&bar_s_full[s], 1);
-      mbar_init(&bar_s_free[s], SPLIT ? 8 : 4);
-      mbar_init(&bar_p_full[s], SPLIT ? 8 : 4);
+      mbar_init(&bar_s_free[s], 4);
+      mbar_init(&bar_p_full[s], 4);
       mbar_init(&bar_p_free[s], 1);
     }
     fence_mbar_init();
@@ -178,7 +174,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         umma_commit(&bar_p_free[st]);
       }
     }
-  } else if constexpr (!SPLIT) {
+  } else {
     const int quad = warp & 3;
     const int r = quad * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
@@ -285,104 +281,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
       }
     }
-  
-  } else {
-    const int quad = warp & 3;              // TMEM lane quadrant (warps 2..9 -> quadrants 2,3,0,1,2,3,0,1)
-    const int half = (warp - 2) >> 2;       // which 32 of the block's 64 keys / of O's 64 columns this thread owns
-    const int r = quad * 32 + lane;         // query row within the tile == TMEM lane (shared by two threads)
-    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
-    float* s_l = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bar_q) + 256);   // [2][128] half-row sums
-    float m_run = -INFINITY, l_run = 0.f;   // l_run: this thread's half of the row sum
-    const int swz = r & 7;
-    for (int j = 0; j < n_blk; ++j) {
-      const int st = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      mbar_wait(&bar_s_full[st], ph);
-      tc_fence_after();
-      uint32_t own[32], oth[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_addr + st * kAttBN + half * 32, own);
-      tmem_ld_32x32b_x32(tmem_base + lane_addr + st * kAttBN + (half ^ 1) * 32, oth);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_s_free[st]);
-      const int kbase = j * kAttBN;
-      if (kbase + kAttBN > L) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (kbase + half * 32 + i >= L) own[i] = 0xff800000u;
-          if (kbase + (half ^ 1) * 32 + i >= L) oth[i] = 0xff800000u;
-        }
-      }
-      // the row max over all 64 keys, computed identically by both threads of the row (no exchange needed)
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(own[i]), __uint_as_float(oth[i])));
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale_log2e;
-      float alpha = 1.0f;
-      if (mx > m_run + 8.0f) {
-        alpha = att_exp2(m_run - mx);
-        m_run = mx;
-      }
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-        // both warps of a quadrant take this branch together (same rows, same maxima); each rescales its 32 columns
-        mbar_wait(&bar_p_free[(j - 1) & 1], ((j - 1) >> 1) & 1);
-        tc_fence_after();
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(tmem_o + lane_addr + half * 32, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st_32x32b_x32(tmem_o + lane_addr + half * 32, o);
-        tmem_st_wait();
-      }
-      mbar_wait(&bar_p_free[st], ph ^ 1);
-      uint8_t* p_row = sP + st * kAttTileBytes + r * 128;
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t packed[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float p0 = att_exp2(fmaf(__uint_as_float(own[2 * i]), scale_log2e, -m_run));
-        const float p1 = att_exp2(fmaf(__uint_as_float(own[2 * i + 1]), scale_log2e, -m_run));
-        rs4[i & 3] += p0 + p1;
-        __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
-        packed[i] = *reinterpret_cast<uint32_t*>(&b);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(p_row + (((half * 4 + q) ^ swz) * 16)) =
-            make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p_full[st]);
-    }
-    // row sum = the two halves; then O / l for this thread's 32 columns
-    s_l[half * 128 + r] = l_run;
-    named_bar_sync(1, 256);
-    const float inv = 1.f / (s_l[r] + s_l[128 + r]);
-    mbar_wait(&bar_p_free[(n_blk - 1) & 1], ((n_blk - 1) >> 1) & 1);
-    tc_fence_after();
-    const int row = q0 + r;
-    uint32_t o[32];
-    tmem_ld_32x32b_x32(tmem_o + lane_addr + half * 32, o);
-    tmem_ld_wait();
-    if (row < L) {
-      __nv_bfloat16* dst = ctx + int64_t(start + row) * H + head * kAttDH + half * 32;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(o[q * 8 + 2 * i]) * inv,
-                                                   __uint_as_float(o[q * 8 + 2 * i + 1]) * inv);
-          w[i] = *reinterpret_cast<uint32_t*>(&b);
-        }
-        *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    }
   }
 
   tc_fence_before();
@@ -401,17 +299,17 @@ int launch_attention_tc(const void* qkv, const int32_t* cu_seqlens, int n_seqs, 
   if (rc != CRAG_OK) return rc;
   const dim3 grid((max_len + kAttBM - 1) / kAttBM, heads, n_seqs);
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(kAttDH));
-  // A/B switch for the SPLIT variant: bit 0 of CRAG_ATTN_VARIANT (read once).  Unset = the validated kernel.
-  static const int env_variant = [] { const char* e = getenv("CRAG_ATTN_VARIANT"); return e ? atoi(e) : 0; }();
-  if (env_variant & 1) {
-    CRAG_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAttSmemBytesSplit)));
-    attention_tc_kernel<true><<<grid, kAttThreadsSplit, kAttSmemBytesSplit, stream>>>(tm_q, tm_kv, cu_seqlens, H, scale_log2e,
-                                                                                      static_cast<__nv_bfloat16*>(ctx));
-  } else {
-    CRAG_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAttSmemBytes)));
-    attention_tc_kernel<false><<<grid, kAttThreads, kAttSmemBytes, stream>>>(tm_q, tm_kv, cu_seqlens, H, scale_log2e,
-                                                                             static_cast<__nv_bfloat16*>(ctx));
+  {  // once per device, not per launch
+    static bool done[64] = {false};
+    int dev = 0;
+    CRAG_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+      CRAG_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kAttSmemBytes)));
+      if (dev >= 0 && dev < 64) done[dev] = true;
+    }
   }
+  attention_tc_kernel<<<grid, kAttThreads, kAttSmemBytes, stream>>>(tm_q, tm_kv, cu_seqlens, H, scale_log2e,
+                                                                    static_cast<__nv_bfloat16*>(ctx));
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }

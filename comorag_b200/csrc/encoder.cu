@@ -160,7 +160,7 @@ extern "C" int crag_attention_varlen(const void* qkv, const int32_t* cu_seqlens,
 extern "C" int crag_attention_varlen_tc(const void* qkv, const int32_t* cu_seqlens, int n_seqs, int total_tokens,
                                         int max_seqlen, int hidden_size, int heads, void* ctx, crag_stream_t stream) {
   if (!qkv || !cu_seqlens || !ctx) return fail(CRAG_ERR_INVALID, "attention: null pointer");
-  heads &= 0xFF;
+  if (heads > 255) return fail(CRAG_ERR_INVALID, "attention_tc: heads must be <= 255 (heads=%d)", heads);
   if (heads < 1 || hidden_size % heads || hidden_size / heads != 64) return fail(CRAG_ERR_UNSUPPORTED, "attention_tc: head dim must be 64");
   return launch_attention_tc(qkv, cu_seqlens, n_seqs, total_tokens, max_seqlen, hidden_size, heads, ctx,
                              static_cast<cudaStream_t>(stream));

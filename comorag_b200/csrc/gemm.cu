@@ -163,27 +163,12 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
 // (full 32-byte sectors) instead of 32 rows x 16 B.  `stage` is this warp's private 32 x 80 B tile.
 constexpr int kEpiStagePitch = 80;
 constexpr int kEpiStageBytes = 32 * kEpiStagePitch;
-// Residual vectors of one 32-column chunk of this thread's row, fetched ahead of use by the pipelined epilogue
-// (PIPE variant): 4 x 16 B, zero where the row / columns fall outside the matrix.
-struct ResidualChunk {
-  uint4 v[4];
-};
-__device__ __forceinline__ void load_residual_chunk(ResidualChunk& rc, const __nv_bfloat16* __restrict__ residual,
-                                                    int64_t ldr, int row, int col0, int M, int N) {
-#pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    rc.v[v] = make_uint4(0u, 0u, 0u, 0u);
-    if (row < M && col0 + v * 8 < N)
-      rc.v[v] = *reinterpret_cast<const uint4*>(residual + int64_t(row) * ldr + col0 + v * 8);
-  }
-}
-
-template <int EPI, bool PRE = false>
+template <int EPI>
 __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&r)[32], int row, int row_base, int col0, int M,
                                                       int N, const float* __restrict__ bias,
                                                       const __nv_bfloat16* __restrict__ residual, int64_t ldr,
                                                       __nv_bfloat16* __restrict__ out, int64_t ldo, uint8_t* stage,
-                                                      int lane, const ResidualChunk* pre = nullptr) {
+                                                      int lane) {
   if (col0 >= N) return;  // warp-uniform
   const bool row_ok = row < M;
   const __nv_bfloat16* rrow = (EPI == GEMM_EPI_BIAS_RESIDUAL) ? residual + int64_t(row) * ldr + col0 : nullptr;
@@ -207,16 +192,6 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&r)[32], i
         for (int j = 0; j < 8; j += 2) gelu_erf2(x[j], x[j + 1]);
       }
       if (EPI == GEMM_EPI_BIAS_RESIDUAL) {
-        if constexpr (PRE) {
-          const uint4 rv = pre->v[v];   // zero outside the matrix
-          const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-            x[2 * j] += __bfloat162float(p.x);
-            x[2 * j + 1] += __bfloat162float(p.y);
-          }
-        } else {
         if (row_ok) {
           const uint4 rv = *reinterpret_cast<const uint4*>(rrow + v * 8);
           const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
@@ -226,7 +201,6 @@ __device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&r)[32], i
             x[2 * j] += __bfloat162float(p.x);
             x[2 * j + 1] += __bfloat162float(p.y);
           }
-        }
         }
       }
       o.x = pack_bf16x2(x[0], x[1]);
@@ -416,10 +390,11 @@ struct Gemm2Layout {
   }
 };
 
-// PIPE = true (A/B variant, bit 2 of the variant word; not dispatched by default and NOT yet validated on hardware):
-// the epilogue keeps the NEXT 32-column tcgen05.ld in flight while it works on the current chunk (two register
-// buffers) instead of exposing the TMEM read latency once per chunk.
-template <int BN, int STAGES, int EPI, int EPI_WARPS, bool PIPE = false>
+// EPI_WARPS = 16 (four warps per lane quadrant, 64 columns each) is used for the GELU epilogue, which is issue-bound:
+// measured on B200 at M=16384, N=4096, K=1024: 1138 -> 1262 TFLOP/s; the residual epilogue gains nothing from it.
+// (A software-pipelined epilogue -- next tcgen05.ld and residual rows in flight during the current chunk -- was
+// measured in round 2 and removed: no gain at K=4096, 12 % slower at N=K=1024.)
+template <int BN, int STAGES, int EPI, int EPI_WARPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
                   int K, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, int64_t ldr,
@@ -528,35 +503,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + col_begin;
-      if constexpr (!PIPE) {
 #pragma unroll 1
       for (int c = 0; c < kColsPerWarp / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c * 32, r);
         tmem_ld_wait();
         epilogue_chunk_staged<EPI>(r, row, row_base, n0 + c * 32, M, N, bias, residual, ldr, out, ldo, stage, lane);
-      }
-      } else {
-        constexpr int kChunks = kColsPerWarp / 32;
-        static_assert(kChunks % 2 == 0, "the pipelined epilogue walks the chunks in pairs");
-        constexpr bool kRes = EPI == GEMM_EPI_BIAS_RESIDUAL;
-        uint32_t ra[32], rb[32];
-        ResidualChunk qa, qb;                                      // residual rows travel one chunk ahead as well
-        tmem_ld_32x32b_x32(t_addr, ra);
-        if constexpr (kRes) load_residual_chunk(qa, residual, ldr, row, n0, M, N);
-#pragma unroll 1
-        for (int c = 0; c < kChunks; c += 2) {
-          tmem_ld_wait_regs(ra);                                   // chunk c has landed
-          tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, rb);          // chunk c+1 in flight during chunk c's math
-          if constexpr (kRes) load_residual_chunk(qb, residual, ldr, row, n0 + (c + 1) * 32, M, N);
-          epilogue_chunk_staged<EPI, kRes>(ra, row, row_base, n0 + c * 32, M, N, bias, residual, ldr, out, ldo, stage, lane, &qa);
-          tmem_ld_wait_regs(rb);
-          if (c + 2 < kChunks) {
-            tmem_ld_32x32b_x32(t_addr + (c + 2) * 32, ra);
-            if constexpr (kRes) load_residual_chunk(qa, residual, ldr, row, n0 + (c + 2) * 32, M, N);
-          }
-          epilogue_chunk_staged<EPI, kRes>(rb, row, row_base, n0 + (c + 1) * 32, M, N, bias, residual, ldr, out, ldo, stage, lane, &qb);
-        }
       }
       tc_fence_before();
       __syncwarp();
@@ -574,13 +526,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (warp == 1) tmem_dealloc_2cta(tmem_base, kTmemCols);
 }
 
-template <int BN, int STAGES, int EPI, int EPI_WARPS, bool PIPE = false>
+template <int BN, int STAGES, int EPI, int EPI_WARPS>
 static int launch_gemm2_t(const CUtensorMap& tm_a, const CUtensorMap& tm_b, int M, int N, int K, const float* bias,
                           const __nv_bfloat16* residual, int64_t ldr, __nv_bfloat16* out, int64_t ldo,
                           cudaStream_t stream) {
   using L = Gemm2Layout<BN, STAGES>;
-  auto kern = gemm2_bf16_kernel<BN, STAGES, EPI, EPI_WARPS, PIPE>;
-  CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L::smem_bytes(EPI_WARPS))));
+  auto kern = gemm2_bf16_kernel<BN, STAGES, EPI, EPI_WARPS>;
+  {  // once per kernel and device, not per launch
+    static bool done[64] = {false};
+    int dev = 0;
+    CRAG_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+      CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L::smem_bytes(EPI_WARPS))));
+      if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+  }
   const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
   int sms = sm_count();
   if (sms <= 0) sms = 148;
@@ -591,14 +551,14 @@ static int launch_gemm2_t(const CUtensorMap& tm_a, const CUtensorMap& tm_b, int 
   return CRAG_OK;
 }
 
-template <int BN, int STAGES, bool PIPE = false>
+template <int BN, int STAGES>
 static int launch_gemm2_e(int epi, const CUtensorMap& tm_a, const CUtensorMap& tm_b, int M, int N, int K,
                           const float* bias, const __nv_bfloat16* residual, int64_t ldr, __nv_bfloat16* out,
                           int64_t ldo, cudaStream_t stream) {
   switch (epi) {
-    case GEMM_EPI_BIAS: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS, 4, PIPE>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
-    case GEMM_EPI_BIAS_GELU: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS_GELU, 8, PIPE>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
-    case GEMM_EPI_BIAS_RESIDUAL: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS_RESIDUAL, 8, PIPE>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
+    case GEMM_EPI_BIAS: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS, 4>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
+    case GEMM_EPI_BIAS_GELU: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS_GELU, 8>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
+    case GEMM_EPI_BIAS_RESIDUAL: return launch_gemm2_t<BN, STAGES, GEMM_EPI_BIAS_RESIDUAL, 8>(tm_a, tm_b, M, N, K, bias, residual, ldr, out, ldo, stream);
   }
   return fail(CRAG_ERR_INVALID, "gemm: unknown epilogue %d", epi);
 }
@@ -625,19 +585,9 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const floa
     // CTA-pair kernel: each CTA fetches half of the W tile
     rc = make_tmap_bf16_2d(&tm_b, w, uint64_t(N), uint64_t(K), uint64_t(ldw) * 2, wide ? 128 : 64);
     if (rc != CRAG_OK) return rc;
-    if ((variant & 8) && wide && epi != GEMM_EPI_BIAS) {
-      // A/B switch (unvalidated): 16 epilogue warps (four per TMEM lane quadrant, 64 columns each) for the GELU
-      // (issue-bound) and residual (load-latency-bound) epilogues; one pipeline stage is traded for their staging tiles
-      if (epi == GEMM_EPI_BIAS_GELU) {
-        if (variant & 4) return launch_gemm2_t<256, 5, GEMM_EPI_BIAS_GELU, 16, true>(tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
-        return launch_gemm2_t<256, 5, GEMM_EPI_BIAS_GELU, 16, false>(tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
-      }
-      return launch_gemm2_t<256, 5, GEMM_EPI_BIAS_RESIDUAL, 16, false>(tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
-    }
-    if (variant & 4) {  // A/B switch: pipelined TMEM reads in the epilogue
-      if (wide) return launch_gemm2_e<256, 6, true>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
-      return launch_gemm2_e<128, 8, true>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
-    }
+    // GELU epilogue on the wide tile: 16 epilogue warps, one pipeline stage traded for their staging tiles
+    if (wide && epi == GEMM_EPI_BIAS_GELU && !(variant & 4))
+      return launch_gemm2_t<256, 5, GEMM_EPI_BIAS_GELU, 16>(tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
     if (wide) return launch_gemm2_e<256, 6>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
     return launch_gemm2_e<128, 8>(epi, tm_a, tm_b, M, N, K, bias, res, ldr, o, ldo, stream);
   }
@@ -652,9 +602,8 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const floa
 extern "C" int crag_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias,
                               const void* residual, int64_t ldr, void* out, int64_t ldo, int m, int n, int k,
                               int epilogue, crag_stream_t stream) {
-  // bits 8+ of `epilogue` select a kernel variant for A/B testing: 0 = default dispatch, bit 0 = force single-CTA,
-  // bit 1 = force the BN = 128 tile, bit 2 = pipelined TMEM reads in the CTA-pair epilogue (unvalidated),
-  // bit 3 = 16 epilogue warps for the GELU / residual epilogues (unvalidated)
+  // bits 8+ of `epilogue` select a kernel variant for A/B measurements (tools/gpu_check_encoder.py): 0 = default
+  // dispatch, bit 0 = force single-CTA, bit 1 = force the BN = 128 tile, bit 2 = 8 (not 16) GELU epilogue warps
   return crag::gemm_bf16(a, lda, w, ldw, bias, residual, ldr, out, ldo, m, n, k, epilogue & 0xFF,
                          static_cast<cudaStream_t>(stream), epilogue >> 8);
 }

@@ -36,6 +36,40 @@ constexpr int kEpiThreads = 128;
 constexpr int kAccStages = 16;       // score-tile buffers in TMEM: the scan may run 16 tiles ahead of the select warps
 constexpr uint32_t kTmemCols = kAccStages * kNQ;  // 512 columns = all of TMEM (1 CTA per SM)
 
+// Pooled admission floor.  Every CTA publishes the scores of its current best kPoolM rows per query (after each
+// flush of that query's candidate buffer) in pool[q][cta][kPoolM] (orderable u32, 0 = nothing yet).  Published values
+// are scores of distinct rows of THIS shard (one CTA's j-th best only ever improves, so values read at different
+// times still have distinct rows at least that good), hence the k-th largest of the pooled values is a score that
+// at least k shard rows reach: nothing below it can rank in the top-k.  Each CTA recomputes that k-th value from
+// time to time (tiles 1, 2, 4, 8, ... and every 32nd) and raises its admission thresholds to it, so all CTAs work
+// with (almost) the global k-th best seen so far instead of their private one -- this replaces the separate sample
+// pre-pass of round 1 (two extra launches) and cuts admissions at k = 100 by about two orders of magnitude.
+constexpr int kPoolM = 4;
+constexpr int kPoolMaxCtas = 160;   // 5 uint4 per lane
+
+__device__ __forceinline__ float pooled_floor(const uint32_t* __restrict__ pool_q, int n_ctas, int k, int lane) {
+  uint32_t v[(kPoolMaxCtas / 32) * kPoolM];
+#pragma unroll
+  for (int i = 0; i < kPoolMaxCtas / 32; ++i) {
+    const int c = lane + 32 * i;
+    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+    if (c < n_ctas) x = __ldcg(reinterpret_cast<const uint4*>(pool_q) + c);   // L2: other SMs keep updating it
+    v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+  }
+  // largest T (low 8 bits clear) with count(v >= T) >= k, by bisection on the orderable bits
+  uint32_t t = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 8; --bit) {
+    const uint32_t cand = t | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < (kPoolMaxCtas / 32) * kPoolM; ++i) c += (v[i] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= k) t = cand;
+  }
+  return t ? unorderable_f32(t) : -INFINITY;   // clearing low bits only lowers the value: still a valid floor
+}
+
 template <int KLIST, int CAP, int STAGES>
 struct SearchLayout {
   static constexpr int kKeysPerQuery = KLIST + CAP;
@@ -84,7 +118,7 @@ template <int KLIST, int CAP, int STAGES, bool IVF = false, bool SCORES = false>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_constant__ CUtensorMap tm_q,
                    int n_rows, int num_kb, int nq, int k, const uint64_t* __restrict__ after_keys,
-                   const float* __restrict__ thr_floor, int floor_stride, uint64_t* __restrict__ part_keys,
+                   uint32_t* __restrict__ pool, uint32_t perm_mul, uint64_t* __restrict__ part_keys,
                    float* __restrict__ part_minmax, const typename IvfParam<IVF, SCORES>::type ivf) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -104,7 +138,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   float* red = reinterpret_cast<float*>(cnt + kNQ);        // [4][kNQ][2]
   uint64_t* bnd_key = reinterpret_cast<uint64_t*>(red + 4 * kNQ * 2);  // [kNQ] admit only keys < bnd_key
   float* bnd_f = reinterpret_cast<float*>(bnd_key + kNQ);              // [kNQ] score part of the bound
-  float* floor_f = bnd_f + kNQ;                                        // [kNQ] admission floor from the sample pre-pass
+  float* floor_f = bnd_f + kNQ;                                        // [kNQ] pooled admission floor
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(floor_f + kNQ);
 
   const int warp = threadIdx.x >> 5;
@@ -112,6 +146,15 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   int num_tiles;
   if constexpr (IVF) num_tiles = __ldg(ivf.n_work);
   else num_tiles = (n_rows + kTileRows - 1) / kTileRows;
+
+  // Flat scans walk the tiles in a multiplicative permutation of the row order (perm_mul coprime to num_tiles):
+  // at any moment the CTAs sample the whole shard, so a corpus whose scores drift along the row order (rows appended
+  // in narrative order, planted neighbours in the tail) looks like a random one to the selector.  HBM does not care:
+  // a tile is 256 KB of contiguous rows either way.
+  auto tile_of = [&](int j) -> int {
+    if constexpr (IVF) return j;
+    else return int((uint64_t(uint32_t(j)) * perm_mul) % uint32_t(num_tiles));
+  };
 
   // ------------------------------------------------------------ one-time setup
   if (warp == 0 && lane == 0) {
@@ -136,12 +179,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   for (int i = threadIdx.x; i < kNQ * L::kKeysPerQuery; i += kSearchThreads) keys[i] = 0ull;
   if (threadIdx.x < kNQ) {
     thr_key[threadIdx.x] = 0ull;
-    // A floor is a score that at least k rows of THIS shard are known to reach (the k-th best of a row sample, see
-    // crag_search_topk): nothing below it can be in the top-k, so the selector starts with a tight threshold
-    // instead of admitting every row of the first tiles.
-    const float fl = (thr_floor != nullptr && int(threadIdx.x) < nq) ? thr_floor[size_t(threadIdx.x) * floor_stride] : -INFINITY;
-    floor_f[threadIdx.x] = fl;
-    thr_f[threadIdx.x] = fl;
+    // floor_f: a score at least k rows of THIS shard are known to reach (pooled over all CTAs, see pooled_floor)
+    floor_f[threadIdx.x] = -INFINITY;
+    thr_f[threadIdx.x] = -INFINITY;
     cnt[threadIdx.x] = 0;
     // "search after": rank continuation for k > 128 -- only candidates strictly below the previous pass's last key
     const uint64_t b = (after_keys != nullptr && int(threadIdx.x) < nq) ? after_keys[threadIdx.x] : ~0ull;
@@ -161,7 +201,8 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       const uint64_t pol = policy_evict_first();
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int j = blockIdx.x; j < num_tiles; j += gridDim.x) {
+        const int tile = tile_of(j);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bar_full[stage], kStageBytes);
@@ -212,11 +253,37 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
 #pragma unroll
     for (int q = 0; q < kNQ; ++q) { mn[q] = INFINITY; mx[q] = -INFINITY; }
 
-    // direct first tile needs room for 128 keys per query and no admission bound of any kind
-    const bool direct_first = !IVF && (KLIST + CAP >= 128) && thr_floor == nullptr && after_keys == nullptr;
+    // direct first tile needs room for 128 keys per query and no continuation bound
+    const bool direct_first = !IVF && (KLIST + CAP >= 128) && after_keys == nullptr;
+    // publish this CTA's best kPoolM rows of query q (call after a flush, by the warp that owns q)
+    auto publish = [&](int q) {
+      if (pool != nullptr && lane < kPoolM) {
+        const uint64_t kk = keys[q * L::kKeysPerQuery + lane];
+        if (kk) pool[(size_t(q) * gridDim.x + blockIdx.x) * kPoolM + lane] = uint32_t(kk >> 32);
+      }
+    };
+    // raise the owned queries' thresholds to the pooled floor
+    auto refresh = [&]() {
+      if (pool == nullptr) return;
+      for (int q = ew; q < nq; q += 4) {
+        const float pf = pooled_floor(pool + size_t(q) * gridDim.x * kPoolM, int(gridDim.x), k, lane);
+        if (lane == 0 && pf > floor_f[q]) {
+          floor_f[q] = pf;
+          thr_f[q] = fmaxf(thr_f[q], pf);
+        }
+      }
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int j = blockIdx.x; j < num_tiles; j += gridDim.x, ++it) {
+      const int tile = tile_of(j);
+      // tiles 1, 2, 4, 8, ... and every 32nd: all four warps take the same branch (it is CTA-uniform); the smem
+      // thresholds they update are read again only after the next named barrier
+      if (it > 0 && ((it & (it - 1)) == 0 || (it & 31) == 0)) {
+        refresh();
+        named_bar_sync(1, kEpiThreads);
+      }
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
       uint32_t r[kNQ];
@@ -250,7 +317,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
             const float s = __uint_as_float(r[q]);
             mn[q] = fminf(mn[q], s);
             mx[q] = fmaxf(mx[q], s);
-            if (s >= thr_f[q] && s <= bnd_f[q]) pending |= 1u << q;
+            // the float test rejects almost everything; survivors must also beat the current k-th KEY, so rows that
+            // only tie its score with a larger row id (duplicate-heavy corpora) do not flood the buffer
+            if (s >= thr_f[q] && s <= bnd_f[q] && make_key(s, uint32_t(row)) > thr_key[q]) pending |= 1u << q;
           }
           if (nq < kNQ) pending &= (1u << nq) - 1u;
         }
@@ -269,7 +338,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
               r[q] = __float_as_uint(s);
               mn[q] = fminf(mn[q], s);
               mx[q] = fmaxf(mx[q], s);
-              if (s >= thr_f[q] && s <= bnd_f[q]) pending |= 1u << q;
+              if (s >= thr_f[q] && s <= bnd_f[q] && make_key(s, uint32_t(row)) > thr_key[q]) pending |= 1u << q;
             }
           }
           if (nq < kNQ) pending &= (1u << nq) - 1u;
@@ -278,7 +347,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       // First tile of an unseeded pass: the lists are empty and every row is a candidate.  Skip the reservation
       // protocol (128-way contended atomics, several flush rounds): each row's key goes straight to slot
       // row_in_tile of the query's buffer and one 128-key sort per query builds the list.
-      if (direct_first && tile == int(blockIdx.x)) {
+      if (direct_first && it == 0) {
 #pragma unroll
         for (int q = 0; q < kNQ; ++q)
           keys[q * L::kKeysPerQuery + quad * 32 + lane] =
@@ -290,6 +359,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
             const uint64_t t = thr_key[q];
             thr_f[q] = fmaxf(floor_f[q], t ? key_score(t) : -INFINITY);
           }
+          publish(q);
         }
         named_bar_sync(1, kEpiThreads);
         continue;
@@ -318,6 +388,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
               thr_f[q] = fmaxf(floor_f[q], t ? key_score(t) : -INFINITY);
               cnt[q] = 0;
             }
+            publish(q);
           }
         }
         named_bar_sync(1, kEpiThreads);
@@ -549,6 +620,183 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fused per-shard finalize + cross-rank exchange + global merge for the row-sharded index, over
+// NVLink peer memory instead of an NCCL all-gather launch.  One CTA per query:
+//   1. merge this rank's per-CTA partial lists into the shard's top-k (as merge_topk_kernel does);
+//   2. PUSH the k (id, score) pairs + (min, max) into slot [parity][this rank][q] of EVERY rank's exchange buffer
+//      (peer-mapped symmetric memory: plain stores that travel over NVLink), fence, then release-store the epoch
+//      into flag [parity][this rank][q] of every rank;
+//   3. wait (acquire loads, bounded) until the flags of all `world` ranks for query q show this epoch;
+//   4. merge the world * k candidates now sitting in the LOCAL buffer (ties: source rank, then position == ascending
+//      global id for contiguous ascending shards) and write the global answer.
+// Every rank runs the same kernel for the same query block (a collective), ends with the same answer, and nothing
+// but the 2.8 KB records crosses the links.  Epochs count calls per query slot on the device (graph-replay safe);
+// two parities of slots make reuse safe: a rank can only start writing epoch e+2 after every peer pushed e+1, which
+// each peer does after it finished reading epoch e.
+constexpr int kXMaxWorld = 16;
+constexpr int kXSlotBytes = 128 * 8 + 128 * 4 + 16;   // ids[128] | scores[128] | min, max, pad
+__host__ __device__ inline size_t xchg_slot_off(int parity, int src, int q, int world) {
+  return ((size_t(parity) * world + src) * kNQ + q) * kXSlotBytes;
+}
+__host__ __device__ inline size_t xchg_flags_off(int world) { return size_t(2) * world * kNQ * kXSlotBytes; }
+__host__ __device__ inline size_t xchg_total_bytes(int world) { return xchg_flags_off(world) + size_t(2) * world * kNQ * 8; }
+
+__device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int KLIST, int CAP>
+__global__ void __launch_bounds__(128) finalize_exchange_kernel(const uint64_t* __restrict__ part_keys,
+                                                                const float* __restrict__ part_minmax, int parts,
+                                                                int nq, int k, int64_t row_offset,
+                                                                const uint64_t* __restrict__ peer_bufs, int rank,
+                                                                int world, uint64_t* __restrict__ epochs,
+                                                                int* __restrict__ status,
+                                                                int64_t* __restrict__ out_ids,
+                                                                float* __restrict__ out_scores,
+                                                                float* __restrict__ out_minmax) {
+  constexpr int KPQ = KLIST + CAP;
+  __shared__ uint64_t s_keys[5][KPQ];
+  __shared__ uint64_t s_thr[5];
+  __shared__ float s_mm[2];
+  __shared__ int s_bad;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x;
+  const uint64_t epoch = epochs[q] + 1;
+  const int parity = int(epoch & 1);
+  if (threadIdx.x == 0) s_bad = 0;
+
+  // ---- 1. this shard's top-k for query q (parts may be 0: empty shard)
+  uint64_t bound = 0;
+  for (int p = lane; p < parts; p += 32) {
+    const uint64_t kth = part_keys[(size_t(p) * kNQ + q) * k + (k - 1)];
+    bound = kth > bound ? kth : bound;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t other = shfl_xor_u64(bound, o);
+    bound = other > bound ? other : bound;
+  }
+  const int my_parts = parts > w ? (parts - w + 3) / 4 : 0;
+  select_stream<KLIST, CAP>(s_keys[w], &s_thr[w], lane, k, my_parts * k, bound, [&](int idx) -> uint64_t {
+    const int pl = idx / k, j = idx - pl * k, p = w + 4 * pl;
+    return part_keys[(size_t(p) * kNQ + q) * k + j];
+  });
+  __syncthreads();
+  if (w == 0) {
+    select_stream<KLIST, CAP>(s_keys[4], &s_thr[4], lane, k, 4 * k, 0ull,
+                              [&](int idx) -> uint64_t { return s_keys[idx / k][idx % k]; });
+    float a = INFINITY, b = -INFINITY;
+    for (int p = lane; p < parts; p += 32) {
+      a = fminf(a, part_minmax[(size_t(p) * kNQ + q) * 2 + 0]);
+      b = fmaxf(b, part_minmax[(size_t(p) * kNQ + q) * 2 + 1]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if (lane == 0) { s_mm[0] = a; s_mm[1] = b; }
+  }
+  __syncthreads();
+
+  // ---- 2. push the record into every rank's slot for (parity, this rank, q)
+  const size_t slot = xchg_slot_off(parity, rank, q, world);
+  for (int idx = threadIdx.x; idx < world * k; idx += blockDim.x) {
+    const int d = idx / k, j = idx - d * k;
+    const uint64_t key = s_keys[4][j];
+    uint8_t* base = reinterpret_cast<uint8_t*>(peer_bufs[d]) + slot;
+    reinterpret_cast<int64_t*>(base)[j] = key ? int64_t(key_id(key)) + row_offset : int64_t(-1);
+    reinterpret_cast<float*>(base + 128 * 8)[j] = key ? key_score(key) : -INFINITY;
+  }
+  if (int(threadIdx.x) < world) {
+    float* mm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(peer_bufs[threadIdx.x]) + slot + 128 * 8 + 128 * 4);
+    mm[0] = s_mm[0];
+    mm[1] = s_mm[1];
+  }
+  __threadfence_system();
+  __syncthreads();
+  const size_t flag_idx = (size_t(parity) * world) * kNQ;   // + src * kNQ + q
+  if (int(threadIdx.x) < world) {
+    uint64_t* flags = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(peer_bufs[threadIdx.x]) + xchg_flags_off(world));
+    st_release_sys_u64(flags + flag_idx + size_t(rank) * kNQ + q, epoch);
+  }
+
+  // ---- 3. wait for every rank's record of this epoch (bounded: a missing peer must not hang the GPU)
+  uint8_t* mine = reinterpret_cast<uint8_t*>(peer_bufs[rank]);
+  if (int(threadIdx.x) < world) {
+    const uint64_t* f = reinterpret_cast<const uint64_t*>(mine + xchg_flags_off(world)) + flag_idx + size_t(threadIdx.x) * kNQ + q;
+    const uint64_t t0 = global_timer_ns();
+    while (ld_acquire_sys_u64(f) < epoch) {
+      __nanosleep(64);
+      if (global_timer_ns() - t0 > 4000000000ull) { s_bad = 1; break; }   // 4 s
+    }
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (threadIdx.x == 0) { *status = 1; epochs[q] = epoch; }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      out_ids[size_t(q) * k + j] = -1;
+      out_scores[size_t(q) * k + j] = -INFINITY;
+    }
+    return;
+  }
+
+  // ---- 4. merge the world * k candidates of the local buffer
+  if (w != 0) return;
+  auto cand_id = [&](int src, int j) -> int64_t {
+    return __ldcv(reinterpret_cast<const long long*>(mine + xchg_slot_off(parity, src, q, world)) + j);
+  };
+  auto cand_score = [&](int src, int j) -> float {
+    return __ldcv(reinterpret_cast<const float*>(mine + xchg_slot_off(parity, src, q, world) + 128 * 8) + j);
+  };
+  select_stream<KLIST, CAP>(s_keys[0], &s_thr[0], lane, k, world * k, 0ull, [&](int idx) -> uint64_t {
+    const int src = idx / k, j = idx - src * k;
+    return cand_id(src, j) >= 0 ? make_key(cand_score(src, j), uint32_t(idx)) : 0ull;
+  });
+  for (int j = lane; j < k; j += 32) {
+    const uint64_t key = s_keys[0][j];
+    float sc = -INFINITY;
+    int64_t id = -1;
+    if (key) {
+      const uint32_t ci = key_id(key);
+      sc = key_score(key);
+      id = cand_id(int(ci) / k, int(ci) % k);
+    }
+    out_scores[size_t(q) * k + j] = sc;
+    out_ids[size_t(q) * k + j] = id;
+  }
+  if (out_minmax != nullptr) {
+    float a = INFINITY, b = -INFINITY;
+    if (lane < world) {
+      const float* mm = reinterpret_cast<const float*>(mine + xchg_slot_off(parity, lane, q, world) + 128 * 8 + 128 * 4);
+      a = __ldcv(mm);
+      b = __ldcv(mm + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if (lane == 0) {
+      out_minmax[size_t(q) * 2 + 0] = a;
+      out_minmax[size_t(q) * 2 + 1] = b;
+    }
+  }
+  if (lane == 0) epochs[q] = epoch;
+}
+
 // ------------------------------------------------------------------ host side
 namespace {
 
@@ -556,8 +804,17 @@ struct SearchPlan {
   int grid;
   size_t keys_bytes;    // per 32-query pass
   size_t minmax_bytes;  // per 32-query pass
-  size_t sample_bytes;  // ids + scores of the sample pre-pass (one 32-query pass)
+  size_t pool_bytes;    // pooled-floor table of one 32-query pass (0 when the grid exceeds kPoolMaxCtas)
 };
+
+// multiplier of the tile permutation j -> (j * P) mod num_tiles: near num_tiles / golden ratio, coprime to num_tiles
+uint32_t perm_multiplier(int64_t num_tiles) {
+  if (num_tiles < 4) return 1u;
+  auto gcd = [](uint64_t a, uint64_t b) { while (b) { const uint64_t t = a % b; a = b; b = t; } return a; };
+  uint64_t p = (uint64_t(double(num_tiles) * 0.6180339887498949) | 1ull);
+  while (gcd(p, uint64_t(num_tiles)) != 1) p += 2;
+  return uint32_t(p % uint64_t(num_tiles));
+}
 
 SearchPlan plan_search(int k) {
   SearchPlan p;
@@ -565,19 +822,33 @@ SearchPlan plan_search(int k) {
   if (p.grid <= 0) p.grid = 148;
   p.keys_bytes = ((size_t(p.grid) * kNQ * k * 8) + 255) & ~size_t(255);
   p.minmax_bytes = ((size_t(p.grid) * kNQ * 2 * 4) + 255) & ~size_t(255);
-  p.sample_bytes = ((size_t(kNQ) * k * (8 + 4)) + 255) & ~size_t(255);
+  p.pool_bytes = p.grid <= kPoolMaxCtas ? ((size_t(kNQ) * p.grid * kPoolM * 4 + 255) & ~size_t(255)) : 0;
   return p;
+}
+
+// cudaFuncSetAttribute once per kernel and device instead of on every launch
+template <class Kern>
+int ensure_smem_attr(Kern kern, size_t smem) {
+  static size_t done[64] = {0};
+  int dev = 0;
+  CRAG_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || done[dev] < smem) {
+    CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    if (dev >= 0 && dev < 64) done[dev] = smem;
+  }
+  return CRAG_OK;
 }
 
 template <int KLIST, int CAP, int STAGES>
 int launch_search(const CUtensorMap& tm_corpus, const CUtensorMap& tm_q, int n_rows, int num_kb, int nq, int k,
-                  int grid, const uint64_t* after_keys, const float* thr_floor, int floor_stride, uint64_t* part_keys,
+                  int grid, const uint64_t* after_keys, uint32_t* pool, uint32_t perm_mul, uint64_t* part_keys,
                   float* part_minmax, cudaStream_t stream) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   const size_t smem = L::smem_bytes(num_kb);
   auto kern = search_topk_kernel<KLIST, CAP, STAGES>;
-  CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, n_rows, num_kb, nq, k, after_keys, thr_floor, floor_stride,
+  int rc = ensure_smem_attr(kern, smem);
+  if (rc != CRAG_OK) return rc;
+  kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, n_rows, num_kb, nq, k, after_keys, pool, perm_mul,
                                                part_keys, part_minmax, NoIvfArgs{});
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
@@ -585,12 +856,13 @@ int launch_search(const CUtensorMap& tm_corpus, const CUtensorMap& tm_q, int n_r
 
 template <int KLIST, int CAP, int STAGES>
 int launch_ivf_scan(const CUtensorMap& tm_res, const CUtensorMap& tm_q, int num_kb, int nq, int k, int grid,
-                    uint64_t* part_keys, float* part_minmax, const IvfArgs& ivf, cudaStream_t stream) {
+                    uint32_t* pool, uint64_t* part_keys, float* part_minmax, const IvfArgs& ivf, cudaStream_t stream) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   const size_t smem = L::smem_bytes(num_kb);
   auto kern = search_topk_kernel<KLIST, CAP, STAGES, true>;
-  CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<grid, kSearchThreads, smem, stream>>>(tm_res, tm_q, 0, num_kb, nq, k, nullptr, nullptr, 0, part_keys, part_minmax, ivf);
+  int rc = ensure_smem_attr(kern, smem);
+  if (rc != CRAG_OK) return rc;
+  kern<<<grid, kSearchThreads, smem, stream>>>(tm_res, tm_q, 0, num_kb, nq, k, nullptr, pool, 1u, part_keys, part_minmax, ivf);
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }
@@ -604,7 +876,7 @@ extern "C" size_t crag_search_workspace_bytes(int nq, int k) {
   (void)nq;
   if (k < 1 || k > 128) return 0;
   const SearchPlan p = plan_search(k);
-  return p.keys_bytes + p.minmax_bytes + p.sample_bytes;
+  return p.keys_bytes + p.minmax_bytes + p.pool_bytes;
 }
 
 namespace crag {
@@ -630,23 +902,28 @@ inline int scan_grid(int64_t n_rows, const SearchPlan& plan) {
 
 // one corpus pass for <= 32 queries: per-CTA partial lists into the workspace
 int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_stride, const void* queries, int nq,
-              int k, const uint64_t* after_keys, const float* thr_floor, int floor_stride, void* workspace,
-              const SearchPlan& plan, cudaStream_t stream, bool small_selector = false) {
+              int k, const uint64_t* after_keys, void* workspace, size_t workspace_bytes, const SearchPlan& plan,
+              cudaStream_t stream) {
   const int grid = scan_grid(n_rows, plan);
   if (grid == 0) return CRAG_OK;
   uint64_t* part_keys = static_cast<uint64_t*>(workspace);
   float* part_minmax = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes);
+  // pooled floor: needs its table in the workspace and pays off once a CTA sees more than a couple of tiles
+  uint32_t* pool = nullptr;
+  const int64_t num_tiles = (n_rows + kTileRows - 1) / kTileRows;
+  if (plan.pool_bytes && workspace_bytes >= plan.keys_bytes + plan.minmax_bytes + plan.pool_bytes && num_tiles >= 4 * int64_t(grid)) {
+    pool = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes + plan.minmax_bytes);
+    CRAG_CUDA_OK(cudaMemsetAsync(pool, 0, plan.pool_bytes, stream));
+  }
   CUtensorMap tm_corpus, tm_q;
   int rc = make_tmap_bf16_2d(&tm_corpus, corpus, uint64_t(n_rows), uint64_t(dim), uint64_t(corpus_row_stride) * 2, kTileRows);
   if (rc != CRAG_OK) return rc;
   rc = make_tmap_bf16_2d(&tm_q, queries, uint64_t(nq), uint64_t(dim), uint64_t(dim) * 2, kNQ);
   if (rc != CRAG_OK) return rc;
   const int num_kb = dim / kBlockK;
-  // small selectors (32- / 64-key sorts, one or two more TMA stages) once the admission floor keeps candidates rare
-  if (k <= 16 && (thr_floor != nullptr || small_selector)) return launch_search<16, 16, 9>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
-  if (k <= 32 && (thr_floor != nullptr || small_selector)) return launch_search<32, 32, 8>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
-  if (k <= 64) return launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
-  return launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, thr_floor, floor_stride, part_keys, part_minmax, stream);
+  const uint32_t perm = perm_multiplier(num_tiles);
+  if (k <= 64) return launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, pool, perm, part_keys, part_minmax, stream);
+  return launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, pool, perm, part_keys, part_minmax, stream);
 }
 
 // merge the per-CTA partials of one pass into the final (ids, scores, minmax) of its <= 32 queries
@@ -673,12 +950,13 @@ int finalize_pass(const void* workspace, int64_t n_rows, int nq, int k, int64_t 
 
 // IVF workspace = the flat scan's per-CTA partials, then the per-pass plan
 struct IvfPlan {
-  size_t mask_off, coarse_off, work_off, count_off, total;
+  size_t pool_off, mask_off, coarse_off, work_off, count_off, total;
 };
 IvfPlan plan_ivf(const SearchPlan& sp, int nlist, int64_t total_tiles) {
   auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
   IvfPlan p;
-  p.mask_off = sp.keys_bytes + sp.minmax_bytes;
+  p.pool_off = sp.keys_bytes + sp.minmax_bytes;
+  p.mask_off = p.pool_off + sp.pool_bytes;
   p.coarse_off = p.mask_off + up(size_t(nlist) * 4);
   p.work_off = p.coarse_off + up(size_t(nlist) * kNQ * 4);
   p.count_off = p.work_off + up(size_t(total_tiles) * sizeof(int4));
@@ -732,8 +1010,13 @@ extern "C" int crag_ivf_search(const void* residuals, int64_t n_rows_padded, int
                                             const_cast<float*>(ivf.coarse), const_cast<int4*>(ivf.work), const_cast<int*>(ivf.n_work));
     CRAG_CUDA_OK(cudaGetLastError());
     // every CTA of the grid publishes a (possibly empty) partial list, so the merge always reads sp.grid parts
-    rc = (k <= 64) ? launch_ivf_scan<64, 64, 7>(tm_res, tm_q, num_kb, nqc, k, sp.grid, part_keys, part_minmax, ivf, stream)
-                   : launch_ivf_scan<128, 128, 5>(tm_res, tm_q, num_kb, nqc, k, sp.grid, part_keys, part_minmax, ivf, stream);
+    uint32_t* pool = nullptr;
+    if (sp.pool_bytes) {
+      pool = reinterpret_cast<uint32_t*>(ws + ip.pool_off);
+      CRAG_CUDA_OK(cudaMemsetAsync(pool, 0, sp.pool_bytes, stream));
+    }
+    rc = (k <= 64) ? launch_ivf_scan<64, 64, 7>(tm_res, tm_q, num_kb, nqc, k, sp.grid, pool, part_keys, part_minmax, ivf, stream)
+                   : launch_ivf_scan<128, 128, 5>(tm_res, tm_q, num_kb, nqc, k, sp.grid, pool, part_keys, part_minmax, ivf, stream);
     if (rc != CRAG_OK) return rc;
     rc = finalize_parts(workspace, sp.grid, nqc, k, 0, out_ids + size_t(q0) * k, out_scores + size_t(q0) * k,
                         out_minmax ? out_minmax + size_t(q0) * 2 : nullptr, nullptr, sp, stream);
@@ -751,7 +1034,7 @@ extern "C" int crag_search_scan(const void* corpus, int64_t n_rows, int dim, int
   int rc = check_search_args(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, workspace, workspace_bytes, plan);
   if (rc != CRAG_OK) return rc;
   if (nq > kNQ) return fail(CRAG_ERR_INVALID, "crag_search_scan handles one pass of at most %d queries (nq=%d)", kNQ, nq);
-  return scan_pass(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, nullptr, nullptr, 0, workspace, plan, static_cast<cudaStream_t>(stream));
+  return scan_pass(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, nullptr, workspace, workspace_bytes, plan, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int crag_search_finalize(const void* workspace, size_t workspace_bytes, int64_t n_rows, int nq, int k,
@@ -774,37 +1057,11 @@ extern "C" int crag_search_topk_after(const void* corpus, int64_t n_rows, int di
   int rc = check_search_args(corpus, n_rows, dim, corpus_row_stride, queries, nq, k, workspace, workspace_bytes, plan);
   if (rc != CRAG_OK) return rc;
   if (!out_ids || !out_scores) return fail(CRAG_ERR_INVALID, "search: null output pointer");
-  // Sample pre-pass (first-rank searches over big shards only): score the first tile of every CTA -- one contiguous
-  // block of grid*128 rows, 38 MB at dim 1024, which the full scan then re-reads from L2 -- and take the sample's
-  // k-th best score as the admission floor of the full scan.  The sample rows are rows of the shard, so at least k
-  // rows reach the floor and nothing below it can rank in the top-k; the full scan then admits ~k * (n_rows /
-  // sample_rows) candidates per query in total instead of treating the head of every CTA's stream as candidates.
-  // (A row-strided sample is statistically nicer but reads 2048 scattered 128-byte pieces per CTA; measured
-  // sample-scan times: strided 57 us, contiguous 52 us, contiguous + direct first-tile path 37 us.)
-  // Measured on B200 (32 queries, 1.25M x 1024 rows): k=10 498 -> 443 us, k=100 1042 -> 651 us per search; the
-  // pre-pass itself costs ~55 us (scan + merge), so it is skipped for small query-block x k products.
-  const int64_t sample_rows = int64_t(plan.grid) * kTileRows;
-  const int64_t sample_stride = n_rows / sample_rows;
-  // pays off when the selector work is a visible share of the pass: small shards (multi-GPU strong scaling) or big k
-  const bool use_sample = after_keys == nullptr && sample_stride >= 16 && int64_t(nq < kNQ ? nq : kNQ) * k >= 128 &&
-                          (n_rows <= 2000000 || k >= 32) &&
-                          workspace_bytes >= plan.keys_bytes + plan.minmax_bytes + plan.sample_bytes;
-  int64_t* sample_ids = reinterpret_cast<int64_t*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes + plan.minmax_bytes);
-  float* sample_scores = reinterpret_cast<float*>(sample_ids + size_t(kNQ) * k);
   for (int q0 = 0; q0 < nq; q0 += kNQ) {
     const int nqc = (nq - q0) < kNQ ? (nq - q0) : kNQ;
     const uint8_t* qptr = static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2;
-    const float* floor = nullptr;
-    if (use_sample) {
-      rc = scan_pass(corpus, sample_rows, dim, corpus_row_stride, qptr, nqc, k, nullptr, nullptr, 0, workspace, plan, stream,
-                     /*small_selector=*/false);  // one tile per CTA: the direct first-tile path of the 128-slot selector
-      if (rc != CRAG_OK) return rc;
-      rc = finalize_pass(workspace, sample_rows, nqc, k, 0, sample_ids, sample_scores, nullptr, nullptr, plan, stream);
-      if (rc != CRAG_OK) return rc;
-      floor = sample_scores + (k - 1);   // k-th best sample score of query q at floor[q * k]; -inf if the sample is short
-    }
-    rc = scan_pass(corpus, n_rows, dim, corpus_row_stride, qptr, nqc, k, after_keys ? after_keys + q0 : nullptr, floor, k,
-                   workspace, plan, stream);
+    rc = scan_pass(corpus, n_rows, dim, corpus_row_stride, qptr, nqc, k, after_keys ? after_keys + q0 : nullptr, workspace,
+                   workspace_bytes, plan, stream);
     if (rc != CRAG_OK) return rc;
     rc = finalize_pass(workspace, n_rows, nqc, k, row_offset, out_ids + size_t(q0) * k, out_scores + size_t(q0) * k,
                        out_minmax ? out_minmax + size_t(q0) * 2 : nullptr, last_keys ? last_keys + q0 : nullptr, plan, stream);
@@ -909,14 +1166,15 @@ extern "C" int crag_search_scores(const void* corpus, int64_t n_rows, int dim, i
   using L = SearchLayout<16, 16, 9>;
   auto kern = search_topk_kernel<16, 16, 9, false, true>;
   const size_t smem = L::smem_bytes(num_kb);
-  CRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  rc = ensure_smem_attr(kern, smem);
+  if (rc != CRAG_OK) return rc;
   for (int q0 = 0; q0 < nq; q0 += kNQ) {
     const int nqc = (nq - q0) < kNQ ? (nq - q0) : kNQ;
     CUtensorMap tm_q;
     rc = make_tmap_bf16_2d(&tm_q, static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2, uint64_t(nqc), uint64_t(dim), uint64_t(dim) * 2, kNQ);
     if (rc != CRAG_OK) return rc;
     ScoreArgs sa{out_scores + int64_t(q0) * out_ld, out_ld};
-    kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, int(n_rows), num_kb, nqc, 1, nullptr, nullptr, 0, nullptr,
+    kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, int(n_rows), num_kb, nqc, 1, nullptr, nullptr, 1u, nullptr,
                                                  part_minmax, sa);
     CRAG_CUDA_OK(cudaGetLastError());
     if (out_minmax) {
@@ -924,5 +1182,34 @@ extern "C" int crag_search_scores(const void* corpus, int64_t n_rows, int dim, i
       CRAG_CUDA_OK(cudaGetLastError());
     }
   }
+  return CRAG_OK;
+}
+
+// ------------------------------------------------------------------ fused finalize + exchange (row-sharded index)
+extern "C" size_t crag_exchange_buffer_bytes(int world) {
+  if (world < 1 || world > kXMaxWorld) return 0;
+  return (xchg_total_bytes(world) + 255) & ~size_t(255);
+}
+
+extern "C" int crag_search_finalize_exchange(const void* workspace, size_t workspace_bytes, int64_t n_rows, int nq, int k,
+                                             int64_t row_offset, const uint64_t* peer_bufs, int rank, int world,
+                                             uint64_t* epochs, int* status, int64_t* out_ids, float* out_scores,
+                                             float* out_minmax, crag_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (nq < 1 || nq > kNQ || k < 1 || k > 128) return fail(CRAG_ERR_INVALID, "crag_search_finalize_exchange: bad nq/k (nq=%d k=%d)", nq, k);
+  if (world < 1 || world > kXMaxWorld || rank < 0 || rank >= world) return fail(CRAG_ERR_INVALID, "crag_search_finalize_exchange: bad rank/world (%d/%d)", rank, world);
+  if (!workspace || !peer_bufs || !epochs || !status || !out_ids || !out_scores) return fail(CRAG_ERR_INVALID, "crag_search_finalize_exchange: null pointer");
+  const SearchPlan plan = plan_search(k);
+  if (workspace_bytes < plan.keys_bytes + plan.minmax_bytes) return fail(CRAG_ERR_WORKSPACE, "crag_search_finalize_exchange: workspace too small");
+  const uint64_t* part_keys = static_cast<const uint64_t*>(workspace);
+  const float* part_minmax = reinterpret_cast<const float*>(static_cast<const uint8_t*>(workspace) + plan.keys_bytes);
+  const int parts = scan_grid(n_rows, plan);
+  if (k <= 32)
+    finalize_exchange_kernel<32, 32><<<nq, 128, 0, stream>>>(part_keys, part_minmax, parts, nq, k, row_offset, peer_bufs, rank, world, epochs, status, out_ids, out_scores, out_minmax);
+  else if (k <= 64)
+    finalize_exchange_kernel<64, 64><<<nq, 128, 0, stream>>>(part_keys, part_minmax, parts, nq, k, row_offset, peer_bufs, rank, world, epochs, status, out_ids, out_scores, out_minmax);
+  else
+    finalize_exchange_kernel<128, 128><<<nq, 128, 0, stream>>>(part_keys, part_minmax, parts, nq, k, row_offset, peer_bufs, rank, world, epochs, status, out_ids, out_scores, out_minmax);
+  CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }

@@ -7,6 +7,7 @@ The reference has no distributed code -- this is the exchange ste
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -60,14 +61,95 @@ def merge_partials_reference(ids: torch.Tensor, scores: torch.Tensor, minmax: to
     return out_i, out_s, mm
 
 
+class PeerExchange:
+    """Symmetric exchange buffers for crag_search_finalize_exchange: one buffer per rank, every buffer mapped into
+    every process (torch.distributed._symmetric_memory: cuMem allocations whose handles are swapped through the
+    process group's store), so a kernel on rank r can store straight into rank d's buffer over NVLink.
+
+    `peer_ptrs` is the device address of the [world] pointer table.  `from_local_buffers` builds the same object
+    out of ordinary tensors of ONE process (several "virtual ranks" on one GPU, used by the single-GPU protocol test)."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup], device: torch.device):
+        import torch.distributed._symmetric_memory as symm
+        from . import _native
+        lib = _native.load()
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        nbytes = int(lib.crag_exchange_buffer_bytes(self.world))
+        if nbytes == 0:
+            raise ValueError(f"world size {self.world} is not supported by the peer exchange (max 16)")
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.peer_ptrs = int(self.handle.buffer_ptrs_dev)
+        self.epochs = torch.zeros(32, dtype=torch.int64, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)          # every buffer is zeroed before any rank pushes into it
+
+    @classmethod
+    def from_local_buffers(cls, bufs: List[torch.Tensor], rank: int) -> "PeerExchange":
+        self = cls.__new__(cls)
+        self.world, self.rank = len(bufs), rank
+        self.buf = bufs[rank]
+        self._table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=bufs[0].device)
+        self.peer_ptrs = self._table.data_ptr()
+        self.epochs = torch.zeros(32, dtype=torch.int64, device=bufs[0].device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=bufs[0].device)
+        return self
+
+    def check(self) -> None:
+        if int(self.status.item()) != 0:
+            raise RuntimeError("peer exchange: a rank's record did not arrive within 4 s (see crag_search_finalize_exchange)")
+
+
 class ShardedIndex:
     """One rank's handle on a row-sharded index (world size 1 degenerates to the local DenseIndex)."""
 
-    def __init__(self, local_index, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, local_index, group: Optional[dist.ProcessGroup] = None, exchange: str = "auto"):
+        """exchange: "peer" = fused finalize + exchange + merge kernel over symmetric memory, "nccl" = one
+        all_gather_into_tensor + merge kernel (the formulation north_star names), "auto" = peer when the symmetric
+        memory rendezvous works on this box, else nccl.  Both give every rank the same global answer."""
         self.local = local_index
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.peer: Optional[PeerExchange] = None
+        self.exchange_mode = "none" if self.world == 1 else "nccl"
+        mode = os.environ.get("CRAG_EXCHANGE", exchange)
+        if self.world > 1 and mode in ("auto", "peer") and dist.get_backend(group) == "nccl":
+            ok = torch.zeros(1, dtype=torch.int32, device=local_index.device)
+            try:
+                self.peer = PeerExchange(group, local_index.device)
+                ok += 1
+            except Exception as e:   # no P2P / fabric handles on this box: say so and use the NCCL formulation
+                if mode == "peer":
+                    raise
+                import logging
+                logging.getLogger(__name__).warning("peer exchange unavailable (%r); using the NCCL all-gather", e)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # all ranks or none
+            if int(ok.item()) == 1:
+                self.exchange_mode = "peer"
+            else:
+                self.peer = None
+        self._sessions = {}
+
+    def session(self, nq: int, k: int, use_graph: bool = True):
+        """Reusable CUDA-graph-captured step for (nq <= 32, k <= 128): scan + fused finalize/exchange/merge (peer
+        mode) or scan + finalize + all-gather + merge (nccl mode).  A collective: build and run on all ranks alike."""
+        from .index import SearchSession
+        key = (nq, k, use_graph)
+        s = self._sessions.get(key)
+        if s is None or s.stale():
+            if self.world == 1:
+                s = SearchSession(self.local, nq, k, use_graph=use_graph)
+            elif self.peer is not None:
+                s = SearchSession(self.local, nq, k, exchange=self.peer, world=self.world, use_graph=use_graph)
+            else:
+                s = SearchSession(self.local, nq, k, world=self.world, use_graph=use_graph,
+                                  gather=lambda out, mine: dist.all_gather_into_tensor(out, mine, group=self.group))
+            self._sessions[key] = s
+        return s
 
     def search_device(self, queries_bf16: torch.Tensor, k: int):
         """Every rank passes the SAME query block; every rank returns the same global (ids, scores, minmax).

@@ -115,6 +115,8 @@ class BertEncoderB200:
         self._tensors: List[torch.Tensor] = []  # keeps device storage alive
         self._build(state)
         self._lock = threading.Lock()
+        self._graphs = {}
+        self._graphs_enabled = os.environ.get("CRAG_ENCODER_GRAPHS", "1") != "0"
 
     # -------------------------------------------------------------- weights
     def _dev(self, t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
@@ -217,12 +219,43 @@ class BertEncoderB200:
                 _native.check(rc, "crag_encoder_forward")
         return out_f32 if out_f32 is not None else out_bf16
 
+    def _check_tokens(self, flat: np.ndarray, longest: int) -> None:
+        """The kernels clamp out-of-range ids / positions instead of faulting; a tokenizer / checkpoint mismatch must
+        fail here, loudly, as the reference's embedding lookup would (nn.Embedding index error)."""
+        cfg = self.config
+        if flat.size and (int(flat.min()) < 0 or int(flat.max()) >= cfg.vocab_size):
+            raise ValueError(f"token id out of range for this checkpoint's vocabulary ({cfg.vocab_size} rows): "
+                             f"min {int(flat.min())}, max {int(flat.max())}")
+        if longest > cfg.max_position_embeddings - cfg.position_offset:
+            raise ValueError(f"sequence of {longest} tokens exceeds the position table "
+                             f"({cfg.max_position_embeddings} rows, offset {cfg.position_offset})")
+
     def encode_token_lists(self, seqs: Sequence[Sequence[int]], normalize: bool = True) -> torch.Tensor:
         """List of token-id lists (already with [CLS]/[SEP]) -> fp32 [n, H] on the device."""
         if len(seqs) == 0:
             return torch.empty((0, self.config.hidden_size), dtype=torch.float32, device=self.device)
-        flat, cu, longest = _pack(seqs, self.device)
-        return self.forward_packed(flat, cu, longest, normalize)
+        flat, cu, longest = _flatten(seqs)
+        self._check_tokens(flat, longest)
+        if len(seqs) <= _GRAPH_MAX_SEQS and flat.size <= _GRAPH_BUCKETS[-1] and self._graphs_enabled:
+            return self._forward_graph(flat, cu, normalize)
+        return self.forward_packed(torch.from_numpy(flat).pin_memory().to(self.device, non_blocking=True),
+                                   torch.from_numpy(cu).pin_memory().to(self.device, non_blocking=True), longest, normalize)
+
+    # ---------------------------------------------------- short-batch CUDA graphs
+    # A query-side encode is a handful of short texts (ComoRAG.py:941,953: batch 1; the probe loop: <= 32 probes of
+    # ~20 tokens) and its ~170 kernel launches cost more than their work (round 1: 3.4 ms for 32 x 24 tokens).  Such
+    # batches run through a CUDA graph captured once per token-count bucket: the batch is padded to the bucket
+    # (empty trailing sequences, pad tokens that belong to no sequence), the kernels read the real lengths from
+    # cu_seqlens on the device, and one cudaGraphLaunch replaces the launch train.
+    def _forward_graph(self, flat: np.ndarray, cu: np.ndarray, normalize: bool) -> torch.Tensor:
+        n, T = cu.size - 1, int(flat.size)
+        bucket = next(b for b in _GRAPH_BUCKETS if T <= b)
+        key = (bucket, bool(normalize))
+        with self._lock:
+            g = self._graphs.get(key)
+            if g is None:
+                g = self._graphs[key] = _EncoderGraph(self, bucket, normalize)
+            return g.run(flat, cu, n, T)
 
     # ------------------------------------------------- cross-encoder scoring
     def classify_packed(self, token_ids: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int,
@@ -247,8 +280,63 @@ class BertEncoderB200:
     def classify_token_lists(self, seqs: Sequence[Sequence[int]]) -> torch.Tensor:
         if len(seqs) == 0:
             return torch.empty((0, self.n_labels), dtype=torch.float32, device=self.device)
-        flat, cu, longest = _pack(seqs, self.device)
-        return self.classify_packed(flat, cu, longest)
+        flat, cu, longest = _flatten(seqs)
+        self._check_tokens(flat, longest)
+        return self.classify_packed(torch.from_numpy(flat).pin_memory().to(self.device, non_blocking=True),
+                                    torch.from_numpy(cu).pin_memory().to(self.device, non_blocking=True), longest)
+
+
+_GRAPH_MAX_SEQS = 32
+_GRAPH_BUCKETS = (128, 512, 2048)      # packed-token buckets served by captured graphs
+
+
+class _EncoderGraph:
+    """One captured crag_encoder_forward over static buffers: `bucket` packed tokens, _GRAPH_MAX_SEQS sequences."""
+
+    def __init__(self, enc: "BertEncoderB200", bucket: int, normalize: bool):
+        dev, cfg = enc.device, enc.config
+        self.enc, self.bucket = enc, bucket
+        self.max_seqlen = min(bucket, cfg.max_position_embeddings - cfg.position_offset)
+        self.h_ids = torch.zeros(bucket, dtype=torch.int32).pin_memory()
+        self.h_cu = torch.zeros(_GRAPH_MAX_SEQS + 1, dtype=torch.int32).pin_memory()
+        with torch.cuda.device(dev):
+            self.ids = torch.zeros(bucket, dtype=torch.int32, device=dev)
+            self.cu = torch.zeros(_GRAPH_MAX_SEQS + 1, dtype=torch.int32, device=dev)
+            self.out = torch.zeros((_GRAPH_MAX_SEQS, cfg.hidden_size), dtype=torch.float32, device=dev)
+            ws_bytes = enc.workspace_bytes(bucket)
+            self.ws = torch.zeros((max(ws_bytes, 256),), dtype=torch.uint8, device=dev)
+
+            def launch(stream):
+                rc = enc._lib.crag_encoder_forward(
+                    C.byref(enc._model), self.ids.data_ptr(), self.cu.data_ptr(), _GRAPH_MAX_SEQS, bucket,
+                    self.max_seqlen, 1 if normalize else 0, self.out.data_ptr(), 0, 0, self.ws.data_ptr(), ws_bytes,
+                    stream.cuda_stream)
+                _native.check(rc, "crag_encoder_forward")
+
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                launch(side)                      # warm: lazy module load + function attributes happen outside capture
+            side.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            # thread_local: other host threads (ComoRAG runs up to 16) may allocate while this one captures
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                launch(torch.cuda.current_stream(dev))
+
+    def run(self, flat: np.ndarray, cu: np.ndarray, n: int, T: int) -> torch.Tensor:
+        self.h_ids[:T] = torch.from_numpy(flat)
+        self.h_ids[T:] = 0
+        self.h_cu[: n + 1] = torch.from_numpy(cu)
+        self.h_cu[n + 1:] = T                     # trailing sequences are empty
+        dev = self.enc.device
+        with torch.cuda.device(dev):
+            self.ids.copy_(self.h_ids, non_blocking=True)
+            self.cu.copy_(self.h_cu, non_blocking=True)
+            self.graph.replay()
+            out = self.out[:n].clone()
+        # the pinned staging buffers are reused by the next call: make sure the H2D copies have consumed them
+        torch.cuda.current_stream(dev).synchronize()
+        return out
 
 
 def _flatten(seqs: Sequence[Sequence[int]]):

@@ -254,6 +254,10 @@ class DenseIndex:
                     _native.check(rc, "crag_rank_scores")
         return ids, out
 
+    def session(self, nq: int, k: int, use_graph: bool = True) -> "SearchSession":
+        """A reusable, CUDA-graph-captured search step for (nq, k); see SearchSession."""
+        return SearchSession(self, nq, k, use_graph=use_graph)
+
     def prepare_queries(self, queries) -> torch.Tensor:
         """Host/device float [nq, dim] -> device bf16 [nq, dim_pad]."""
         q = torch.as_tensor(queries)
@@ -283,6 +287,92 @@ class DenseIndex:
             return ids.numpy().copy(), scores.numpy().copy(), minmax.numpy().copy()
         ids, scores, minmax = self.search_device(q, k)
         return ids.cpu().numpy(), scores.cpu().numpy(), minmax.cpu().numpy()
+
+
+class SearchSession:
+    """One search step for a fixed (nq <= 32, k <= 128) over static buffers, captured in a CUDA graph: what a serving
+    loop (the probe batches of ComoRAG's meta loop, ComoRAG.py:354-358) calls again and again.  The step is
+    pool-memset + scan kernel + finalize kernel; with `exchange` (a dist.PeerExchange) the finalize is the fused
+    finalize + cross-rank exchange + merge kernel and every rank ends with the global answer; with `gather` (a
+    callable doing the NCCL all-gather of the packed record) the step is scan + finalize + all-gather + merge.
+
+    run(queries) returns views of the session's output buffers -- valid until the next run()."""
+
+    def __init__(self, index: "DenseIndex", nq: int, k: int, exchange=None, gather=None, world: int = 1,
+                 use_graph: bool = True):
+        if not (1 <= nq <= 32 and 1 <= k <= MAX_K):
+            raise ValueError("SearchSession needs 1 <= nq <= 32 and 1 <= k <= 128")
+        self.index, self.nq, self.k = index, nq, k
+        self.exchange, self.gather, self.world = exchange, gather, world
+        dev = index.device
+        self._lib = _native.load()
+        self._buf, self._n = index._snapshot()
+        with torch.cuda.device(dev):
+            self.queries = torch.zeros((nq, index.dim_pad), dtype=torch.bfloat16, device=dev)
+            self.record = torch.zeros(packed_record_bytes(nq, k), dtype=torch.uint8, device=dev)
+            self.ids, self.scores, self.minmax = packed_views(self.record, nq, k)
+            self._ws_bytes = self._lib.crag_search_workspace_bytes(nq, k)
+            self._ws = torch.zeros((self._ws_bytes,), dtype=torch.uint8, device=dev)
+            if gather is not None:
+                self._gathered = torch.zeros(world * self.record.numel(), dtype=torch.uint8, device=dev)
+                self._local = torch.zeros_like(self.record)
+            self.graph = None
+            if use_graph:
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    self._enqueue(side)                      # warm-up outside capture (also a collective when sharded)
+                side.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._enqueue(torch.cuda.current_stream(dev))
+                self.graph = g
+
+    def _enqueue(self, st) -> None:
+        lib, ix = self._lib, self.index
+        buf, n = self._buf, self._n
+        rc = lib.crag_search_scan(buf.data_ptr() if n else 0, n, ix.dim_pad, buf.stride(0) if buf.shape[0] else ix.dim_pad,
+                                  self.queries.data_ptr(), self.nq, self.k, self._ws.data_ptr(), self._ws_bytes, st.cuda_stream)
+        _native.check(rc, "crag_search_scan")
+        if self.exchange is not None:
+            x = self.exchange
+            rc = lib.crag_search_finalize_exchange(self._ws.data_ptr(), self._ws_bytes, n, self.nq, self.k, ix.row_offset,
+                                                   x.peer_ptrs, x.rank, x.world, x.epochs.data_ptr(), x.status.data_ptr(),
+                                                   self.ids.data_ptr(), self.scores.data_ptr(), self.minmax.data_ptr(),
+                                                   st.cuda_stream)
+            _native.check(rc, "crag_search_finalize_exchange")
+            return
+        out = packed_views(self._local, self.nq, self.k) if self.gather is not None else (self.ids, self.scores, self.minmax)
+        rc = lib.crag_search_finalize(self._ws.data_ptr(), self._ws_bytes, n, self.nq, self.k, ix.row_offset,
+                                      out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), st.cuda_stream)
+        _native.check(rc, "crag_search_finalize")
+        if self.gather is not None:
+            self.gather(self._gathered, self._local)
+            per = self._local.numel()
+            rc = lib.crag_merge_topk_packed(self._gathered.data_ptr(), per, self.world, self.nq, self.k, self.ids.data_ptr(),
+                                            self.scores.data_ptr(), self.minmax.data_ptr(), st.cuda_stream)
+            _native.check(rc, "crag_merge_topk_packed")
+
+    def stale(self) -> bool:
+        """True when the index grew or moved since the session was built (the tensor maps in the graph are baked)."""
+        buf, n = self.index._snapshot()
+        return n != self._n or buf.data_ptr() != self._buf.data_ptr()
+
+    def run(self, queries: torch.Tensor):
+        """queries: bf16 [nq, dim_pad] (device) or anything DenseIndex.prepare_queries accepts."""
+        if self.stale():
+            raise RuntimeError("the index changed since this SearchSession was built; build a new one")
+        if not (queries.is_cuda and queries.dtype == torch.bfloat16):
+            queries = self.index.prepare_queries(queries)
+        dev = self.index.device
+        with torch.cuda.device(dev):
+            if queries.data_ptr() != self.queries.data_ptr():
+                self.queries.copy_(queries, non_blocking=True)
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._enqueue(torch.cuda.current_stream(dev))
+        return self.ids, self.scores, self.minmax
 
 
 def merge_topk(scores: torch.Tensor, ids: torch.Tensor, minmax: Optional[torch.Tensor]):

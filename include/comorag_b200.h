@@ -128,6 +128,24 @@ CRAG_API int crag_merge_topk(const float* scores, const int64_t* ids, const floa
 CRAG_API int crag_merge_topk_packed(const void* records, int64_t record_bytes, int parts, int nq, int k,
                                     int64_t* out_ids, float* out_scores, float* out_minmax, crag_stream_t stream);
 
+/* Row-sharded index, exchange step WITHOUT a collective-library launch: the per-shard
+ * finalize, the cross-rank exchange and the global merge as ONE kernel over NVLink peer memory.  After
+ * crag_search_scan on every rank (same query block, nq <= 32), every rank calls this with
+ *   peer_bufs  device array [world] of pointers to each rank's exchange buffer as mapped in THIS process (symmetric
+ *              memory: entry `rank` is the local buffer); each buffer is crag_exchange_buffer_bytes(world) bytes and
+ *              zero-filled once before its first use
+ *   epochs     device u64 [32], zero-filled once; counts calls per query slot (owned by the library afterwards)
+ *   status     device int, set to 1 if a peer's record did not arrive within 4 s (outputs are then id -1 / -inf)
+ * One CTA per query merges the shard's per-CTA partials, stores its k (id, score) pairs + (min, max) into every
+ * rank's buffer, release-signals, waits for all ranks' records and merges them: every rank ends with the same
+ * global (ids, scores, minmax) as crag_search_topk + all-gather + crag_merge_topk_packed would give.  A collective:
+ * all ranks of the group must call it, in the same order, one call at a time per buffer. */
+CRAG_API size_t crag_exchange_buffer_bytes(int world);
+CRAG_API int crag_search_finalize_exchange(const void* workspace, size_t workspace_bytes, int64_t n_rows, int nq, int k,
+                                           int64_t row_offset, const uint64_t* peer_bufs, int rank, int world,
+                                           uint64_t* epochs, int* status, int64_t* out_ids, float* out_scores,
+                                           float* out_minmax, crag_stream_t stream);
+
 /* Score-all pass: raw inner products of EVERY shard row, for the reference's full-array contracts --
  *     query_fact_scores = np.dot(self.fact_embeddings, q.T)            (ComoRAG.py:944; get_fact_scores returns all
  *                                                                      N_f scores and callers index them, :475,:1054)

@@ -234,3 +234,191 @@ def test_retrieve_knn_matches_reference_golden(dev):
     assert overlap > 0.97
     big = retrieve_knn(["a"], [f"k{i}" for i in range(len(K))], Q[:1], K, k=2047, device=dev)   # reference default k
     assert len(big["a"][0]) == 2047 and len(set(big["a"][0])) == 2047 and np.all(np.diff(big["a"][1]) <= 0)
+
+
+@pytest.mark.parametrize("n,dim,nq", [(1, 64, 1), (127, 64, 3), (1000, 128, 33), (20001, 1024, 32), (300000, 768, 2)])
+def test_score_all_pass_equals_the_dot_products(dev, n, dim, nq):
+    """crag_search_scores = np.dot(E, q.T) of ComoRAG.py:944,958-960 for every row (fp32 accumulate on the tensor
+    cores), plus the (min, max) the reference's min_max_normalize takes over that array."""
+    corpus, queries = make_unit_rows(n, dim, 500 + n, device=dev), make_unit_rows(nq, dim, 600 + n, device=dev)
+    idx = _index(corpus, dev)
+    scores, minmax = idx.scores_device(queries)
+    assert scores.shape == (nq, n)
+    want = queries.double() @ corpus.double().T
+    assert (scores.double() - want).abs().max().item() < 2e-6
+    assert torch.equal(minmax[:, 0], scores.min(dim=1).values) and torch.equal(minmax[:, 1], scores.max(dim=1).values)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 2049, 70001, (1 << 21) + 3])
+def test_rank_scores_is_a_stable_descending_sort(dev, n):
+    """crag_rank_scores = np.argsort(scores)[::-1] with ties by ascending row: duplicates, signed zeros, infinities."""
+    from comorag_b200.index import DenseIndex
+    g = torch.Generator(device=dev).manual_seed(n)
+    s = torch.randn(n, generator=g, device=dev)
+    s = (s * 8).round() / 8 if n > 100 else s            # many exact duplicates
+    if n > 40:
+        s[3], s[7], s[11], s[13], s[17] = 0.0, -0.0, float("inf"), float("-inf"), 0.0
+    idx = DenseIndex(64, device=dev)
+    ids, out = idx.rank_device(s.contiguous())
+    order = torch.argsort(s, descending=True, stable=True)
+    # -0.0 == 0.0 for torch's comparison but the radix key orders +0 before -0; both are valid descending orders,
+    # so compare scores exactly and ids wherever the score is not a zero
+    assert torch.equal(out, s[ids]) and (out[:-1] >= out[1:]).all()
+    nz = s[order] != 0
+    assert torch.equal(ids[nz], order[nz])
+    assert sorted(ids.tolist()) == list(range(n)) if n < 5000 else ids.unique().numel() == n
+
+
+def test_full_ranking_contract_at_two_million_rows(dev):
+    """dense_passage_retrieval's full permutation (ComoRAG.py:965) and get_fact_scores' full array (ComoRAG.py:948)
+    on a 2M x 256 shard: one score-all pass + one device sort, equal to the reference expressions evaluated in
+    float64 on the same bf16 rows (ties and near-ties compared through the scores)."""
+    from comorag_b200.retrieval import dense_passage_retrieval, get_fact_scores, min_max_normalize
+    n, dim = 2_000_000, 256
+    corpus, q = make_unit_rows(n, dim, 77, device=dev), make_unit_rows(1, dim, 78, device=dev)
+    idx = _index(corpus, dev)
+    order, sc = dense_passage_retrieval(idx, q.float().cpu().numpy())
+    want = (q.double() @ corpus.double().T)[0].cpu().numpy()
+    want_norm = min_max_normalize(want)
+    assert order.dtype == np.int64 and order.shape == (n,) and np.array_equal(np.sort(order), np.arange(n))
+    assert np.all(np.diff(sc) <= 0) and np.abs(sc - want_norm[order]).max() < 1e-5
+    ref_order = np.argsort(want_norm)[::-1]
+    assert np.abs(want_norm[ref_order] - want_norm[order]).max() < 1e-5      # same ranking up to fp32 near-ties
+    clear = np.flatnonzero((np.abs(np.diff(want_norm[ref_order][:102])) > 1e-5)[:-1] & (np.abs(np.diff(want_norm[ref_order][:102])) > 1e-5)[1:]) + 1
+    assert np.array_equal(order[clear], ref_order[clear])                     # ranks with clear gaps on both sides: same row
+    facts = get_fact_scores(idx, q.float().cpu().numpy())
+    assert facts.shape == (n,) and facts.dtype == np.float32 and np.abs(facts - want_norm).max() < 1e-5
+    assert facts.max() == 1.0 and facts.min() == 0.0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Parity AT the headline shape (BASELINE configs 2/3: 10M x 1024, 32 probe queries) and on adversarially ordered
+# corpora, through the same C-ABI entry point bench.py times.
+def _timed_search(index, queries, k, reps=5):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    out = index.search_device(queries, k)       # warm (tensor maps, function attributes)
+    torch.cuda.synchronize()
+    for a, b in ev:
+        a.record()
+        out = index.search_device(queries, k)
+        b.record()
+    torch.cuda.synchronize()
+    return out, sorted(a.elapsed_time(b) for a, b in ev)[reps // 2]
+
+
+@pytest.mark.parametrize("k", [10, 100])
+def test_headline_shape_10m_rows_ids_exact(dev, k):
+    """10M x 1024 bf16, 32 queries, k = 10 (configs 2/3/5) and 100 (config 4): ids bit-exact against the float64
+    ranking of the same bf16 rows (near-ties below 2e-6 as sets), scores within 1e-3, (min, max) exact to 1e-5."""
+    from comorag_b200.index import DenseIndex
+    n, dim, nq = 10_000_000, 1024, 32
+    corpus = make_unit_rows(n, dim, 1234, device=dev)
+    queries = make_unit_rows(nq, dim, 4321, device=dev)
+    idx = DenseIndex.from_tensor(corpus)
+    (ids, scores, mm), ms = _timed_search(idx, queries, k)
+    want_i, want_s, want_mm, gaps = torch_reference_topk(corpus, queries, k)
+    so.assert_topk_matches(ids.cpu().numpy(), scores.double().cpu().numpy(), want_i, want_s, gaps, score_tol=1e-3)
+    np.testing.assert_allclose(mm.cpu().numpy(), want_mm, atol=1e-5)
+    # 20.48 GB per pass: anything slower than 4 ms (5.1 TB/s) means the selector, not HBM, set the pace
+    assert ms < 4.0, f"10M x 1024 top-{k} pass took {ms:.2f} ms"
+
+
+def _adversarial_corpus(kind, n, dim, queries, dev):
+    g = torch.Generator(device=dev).manual_seed(2024)
+    base = torch.randn((n, dim), generator=g, device=dev, dtype=torch.float32)
+    qf = queries.float()
+    if kind == "ascending":          # every query's score drifts upward with the row id (rows appended in story order)
+        u = torch.nn.functional.normalize(qf.mean(dim=0), dim=0)
+        a = torch.linspace(0.0, 0.8, n, device=dev)[:, None]
+        base = torch.nn.functional.normalize(base, dim=1) * (1 - a * a).sqrt() + a * u[None, :]
+    elif kind == "planted_tail":     # SURVEY 8d: x_j = normalise(q + 0.3 noise), 64 rows per query, all in the last tiles
+        per = 64
+        tail = qf.repeat_interleave(per, dim=0) + 0.3 * torch.randn((qf.shape[0] * per, dim), generator=g, device=dev)
+        base[n - tail.shape[0]:] = tail
+    elif kind == "duplicates":       # one row repeated: every score ties, ranks must be rows 0..k-1
+        base = base[:1].expand(n, dim).clone()
+    elif kind == "query_is_a_row":   # self-retrieval: row 777_777 + 37 * q is query q itself
+        pass
+    rows = torch.nn.functional.normalize(base, dim=1).to(torch.bfloat16)
+    if kind == "query_is_a_row":
+        for q in range(queries.shape[0]):
+            rows[777_777 + 37 * q] = queries[q]
+    return rows
+
+
+@pytest.mark.parametrize("kind", ["ascending", "planted_tail", "duplicates", "query_is_a_row"])
+@pytest.mark.parametrize("k", [10, 100])
+def test_adversarial_row_orders_exact_and_not_slower(dev, kind, k):
+    """>= 1M rows whose order is hostile to a streaming selector: ids exact AND the pass is not slower than 1.3x the
+    same-shape random corpus (the tile permutation + pooled floor are what keep admissions rare here)."""
+    from comorag_b200.index import DenseIndex
+    n, dim, nq = 1_500_000, 1024, 32
+    queries = make_unit_rows(nq, dim, 4321, device=dev)
+    random_idx = DenseIndex.from_tensor(make_unit_rows(n, dim, 99, device=dev))
+    _, ms_random = _timed_search(random_idx, queries, k)
+    del random_idx
+    corpus = _adversarial_corpus(kind, n, dim, queries, dev)
+    idx = DenseIndex.from_tensor(corpus)
+    (ids, scores, mm), ms = _timed_search(idx, queries, k)
+    want_i, want_s, want_mm, gaps = torch_reference_topk(corpus, queries, k)
+    so.assert_topk_matches(ids.cpu().numpy(), scores.double().cpu().numpy(), want_i, want_s, gaps, score_tol=1e-3)
+    np.testing.assert_allclose(mm.cpu().numpy(), want_mm, atol=1e-5)
+    if kind == "duplicates":
+        np.testing.assert_array_equal(ids.cpu().numpy(), np.tile(np.arange(k), (nq, 1)))
+    if kind == "query_is_a_row":
+        assert (ids[:, 0].cpu().numpy() == 777_777 + 37 * np.arange(nq)).all()
+    assert ms <= 1.3 * ms_random + 0.02, f"{kind}: {ms:.3f} ms vs {ms_random:.3f} ms on a random corpus"
+
+
+@pytest.mark.parametrize("nq,k", [(32, 10), (5, 100), (1, 1)])
+def test_search_session_graph_replay_matches_direct_search(dev, nq, k):
+    """The CUDA-graph-captured step (static buffers, replayed) returns what crag_search_topk returns, for changing
+    query blocks, and refuses to run once the index has grown."""
+    from comorag_b200.index import DenseIndex
+    idx = DenseIndex(256, device=dev, capacity=400_000)
+    idx.add(make_unit_rows(300_000, 256, 5, device=dev))
+    sess = idx.session(nq, k)
+    for seed in (1, 2, 3):
+        q = make_unit_rows(nq, 256, 900 + seed, device=dev)
+        ids, scores, mm = (t.clone() for t in sess.run(q))
+        d_ids, d_scores, d_mm = idx.search_device(q, k)
+        assert torch.equal(ids, d_ids) and torch.equal(scores, d_scores) and torch.equal(mm, d_mm)
+    idx.add(make_unit_rows(10, 256, 6, device=dev))
+    with pytest.raises(RuntimeError):
+        sess.run(q)
+
+
+@pytest.mark.parametrize("world,k", [(2, 10), (4, 100), (8, 10)])
+def test_fused_finalize_exchange_merge_virtual_ranks(dev, world, k):
+    """crag_search_finalize_exchange with `world` virtual ranks on ONE GPU (each rank = its own stream, workspace and
+    exchange buffer; the peer table points at ordinary device tensors): every rank must end with exactly what the
+    unsharded search returns, over several epochs (slot parity reuse), including a rank whose shard is empty."""
+    from comorag_b200 import _native
+    from comorag_b200.dist import PeerExchange, shard_bounds
+    from comorag_b200.index import DenseIndex, SearchSession
+    lib = _native.load()
+    n, dim, nq = 200_000, 128, 32
+    corpus = make_unit_rows(n, dim, 31, device=dev)
+    whole = DenseIndex.from_tensor(corpus)
+    offs = shard_bounds(n, world)
+    if world == 4:                       # make rank 2's shard empty
+        offs[3] = offs[2]
+    nbytes = int(lib.crag_exchange_buffer_bytes(world))
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+    shards = [DenseIndex.from_tensor(corpus[offs[r]:offs[r + 1]], row_offset=offs[r]) if offs[r + 1] > offs[r]
+              else DenseIndex(dim, device=dev, row_offset=offs[r]) for r in range(world)]
+    sessions = [SearchSession(shards[r], nq, k, exchange=PeerExchange.from_local_buffers(bufs, r), world=world, use_graph=False)
+                for r in range(world)]
+    streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    for epoch in range(5):
+        q = make_unit_rows(nq, dim, 700 + epoch, device=dev)
+        torch.cuda.synchronize()
+        outs = []
+        for r in range(world):           # all ranks in flight at once: each kernel waits for the others' records
+            with torch.cuda.stream(streams[r]):
+                outs.append(sessions[r].run(q))
+        torch.cuda.synchronize()
+        want = whole.search_device(q, k)
+        for r in range(world):
+            sessions[r].exchange.check()
+            assert torch.equal(outs[r][0], want[0]) and torch.equal(outs[r][1], want[1]) and torch.equal(outs[r][2], want[2]), (epoch, r)
