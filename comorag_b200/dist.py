@@ -8,6 +8,7 @@ The reference has no distributed code -- this is the exchange ste
 from __future__ import annotations
 
 import os
+import threading
 from typing import List, Optional, Tuple
 
 import torch
@@ -133,6 +134,7 @@ class ShardedIndex:
             else:
                 self.peer = None
         self._sessions = {}
+        self._lock = threading.RLock()      # sessions own static buffers: one search at a time per ShardedIndex
 
     def session(self, nq: int, k: int, use_graph: bool = True):
         """Reusable CUDA-graph-captured step for (nq <= 32, k <= 128): scan + fused finalize/exchange/merge (peer
@@ -151,22 +153,34 @@ class ShardedIndex:
             self._sessions[key] = s
         return s
 
-    def search_device(self, queries_bf16: torch.Tensor, k: int):
+    def search_device(self, queries_bf16: torch.Tensor, k: int, use_graph: bool = True):
         """Every rank passes the SAME query block; every rank returns the same global (ids, scores, minmax).
 
-        Per step: scan kernel + per-shard finalize kernel (writing straight into the packed send record) + ONE
-        all_gather_into_tensor + one merge kernel over the gathered records; no pack/unpack copies."""
-        from .index import merge_topk_packed, packed_record_bytes, packed_views
+        Per block of 32 queries: scan kernel + fused finalize/exchange/merge kernel (peer mode), or scan + finalize +
+        ONE all_gather_into_tensor + merge kernel (nccl mode); each block runs as a captured CUDA graph over the
+        session's static buffers.  k <= 128 (the single-GPU rank continuation is shard-local)."""
         if self.world == 1:
             return self.local.search_device(queries_bf16, k)
+        if k > 128:
+            raise ValueError("ShardedIndex.search_device supports k <= 128 (rank continuation is per shard); "
+                             "merge several shards' paged results on the host for larger k")
         nq = queries_bf16.shape[0]
-        per = packed_record_bytes(nq, k)
-        dev = queries_bf16.device
-        mine = torch.empty(per, dtype=torch.uint8, device=dev)
-        self.local.search_device(queries_bf16, k, out=packed_views(mine, nq, k))
-        gathered = torch.empty(self.world * per, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(gathered, mine, group=self.group)
-        return merge_topk_packed(gathered, self.world, nq, k)
+        outs = []
+        with self._lock:
+            for q0 in range(0, nq, 32):
+                blk = queries_bf16[q0:q0 + 32]
+                sess = self.session(blk.shape[0], k, use_graph)
+                res = sess.run(blk)
+                outs.append(res if nq <= 32 else tuple(t.clone() for t in res))
+        if len(outs) == 1:
+            return outs[0]
+        return tuple(torch.cat([o[i] for o in outs], 0) for i in range(3))
+
+    def search(self, queries, k: int):
+        """Host-buffer entry point on every rank: numpy / torch queries [nq, dim] in, numpy (ids, scores, minmax) out."""
+        q = self.local.prepare_queries(queries)
+        ids, scores, mm = self.search_device(q, k)
+        return ids.cpu().numpy(), scores.cpu().numpy(), mm.cpu().numpy()
 
 
 def pair_bounds(n_pairs: int, world: int) -> List[int]:
@@ -174,7 +188,8 @@ def pair_bounds(n_pairs: int, world: int) -> List[int]:
     return shard_bounds(n_pairs, world)
 
 
-def sharded_rerank(score_fn, token_lists, group: Optional[dist.ProcessGroup] = None, device=None) -> torch.Tensor:
+def sharded_rerank(score_fn, token_lists, group: Optional[dist.ProcessGroup] = None, device=None,
+                   n_labels: Optional[int] = None) -> torch.Tensor:
     """BASELINE config 5 across the GPUs of one box: after the row-sharded search every rank holds the SAME global
     candidate list, so the (query, passage) pairs are split by rank (no data-path collective for the scoring),
     each rank runs its slice through `score_fn(list of token lists) -> float32 [m, n_labels]` (the cross-encoder,
@@ -192,7 +207,14 @@ def sharded_rerank(score_fn, token_lists, group: Optional[dist.ProcessGroup] = N
         mine = mine.to(device)
     if world == 1:
         return mine
-    labels = mine.shape[1]
+    # a rank with an empty slice (fewer pairs than ranks) cannot know the label count from its own (0, ?) output:
+    # agree on it (max over ranks) before sizing the collective
+    lab = torch.tensor([n_labels if n_labels is not None else (mine.shape[1] if mine.shape[0] else 0)],
+                       dtype=torch.int64, device=mine.device)
+    dist.all_reduce(lab, op=dist.ReduceOp.MAX, group=group)
+    labels = max(int(lab.item()), 1)
+    if mine.shape[0] == 0:
+        mine = mine.new_zeros((0, labels))
     per = b[1] - b[0]                      # the largest slice (the first n % world ranks hold one more pair)
     send = torch.zeros((per, labels), dtype=torch.float32, device=mine.device)
     send[: mine.shape[0]] = mine

@@ -85,3 +85,29 @@ def test_two_rank_pair_sharded_rerank(tmp_path, n_pairs):
         np.testing.assert_array_equal(got["logits"], want)
         sizes.append(int(got["seen"][0]))
     assert sum(sizes) == n_pairs and max(sizes) - min(sizes) <= 1
+
+
+def _rerank_worker_labels(rank, world, port, n_pairs, labels, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from comorag_b200.dist import sharded_rerank
+    pairs = [[0, 5 + i, 2] for i in range(n_pairs)]
+
+    def score(token_lists):   # a rank with nothing to score returns shape (0,): it cannot know the label count
+        if not token_lists:
+            return np.zeros((0,), dtype=np.float32)
+        return np.array([[float(t[1]) * (j + 1) for j in range(labels)] for t in token_lists], dtype=np.float32)
+
+    got = sharded_rerank(score, pairs)
+    np.save(os.path.join(out_dir, f"rl{rank}.npy"), got.numpy())
+    dist.destroy_process_group()
+
+
+def test_rerank_label_count_is_agreed_across_ranks(tmp_path):
+    """fewer pairs than ranks + more than one label -- the empty rank must not size the collective from
+    its own (0, 1) output."""
+    world, n_pairs, labels = 2, 1, 3
+    mp.spawn(_rerank_worker_labels, args=(world, _free_port(), n_pairs, labels, str(tmp_path)), nprocs=world, join=True)
+    want = np.array([[5.0, 10.0, 15.0]], dtype=np.float32)
+    for r in range(world):
+        np.testing.assert_array_equal(np.load(tmp_path / f"rl{r}.npy"), want)

@@ -105,6 +105,21 @@ def test_full_score_contracts_on_a_fake_index():
             ids = np.argsort(-sc, axis=1, kind="stable")[:, :k]
             return ids, np.take_along_axis(sc, ids, 1), np.stack([sc.min(1), sc.max(1)], 1)
 
+        # CPU stand-ins for the device entry points of the full-array contracts (score-all pass + device ranking)
+        def prepare_queries(self, queries):
+            import torch
+            return torch.as_tensor(np.asarray(queries, np.float32))
+
+        def scores_device(self, q):
+            import torch
+            sc = q @ torch.from_numpy(E).T
+            return sc, torch.stack([sc.min(1).values, sc.max(1).values], 1)
+
+        def rank_device(self, row):
+            import torch
+            order = torch.argsort(row, descending=True, stable=True)
+            return order, row[order]
+
     ids, scores = rt.dense_passage_retrieval(FakeIndex(), q)
     want_ids, want_scores = so.dense_passage_retrieval(E, q)
     np.testing.assert_array_equal(ids, want_ids)
