@@ -118,7 +118,7 @@ template <int KLIST, int CAP, int STAGES, bool IVF = false, bool SCORES = false>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_constant__ CUtensorMap tm_q,
                    int n_rows, int num_kb, int nq, int k, const uint64_t* __restrict__ after_keys,
-                   uint32_t* __restrict__ pool, uint32_t perm_mul, uint64_t* __restrict__ part_keys,
+                   uint32_t* __restrict__ pool, uint32_t perm_mul, int perm_shift, uint64_t* __restrict__ part_keys,
                    float* __restrict__ part_minmax, const typename IvfParam<IVF, SCORES>::type ivf) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -147,13 +147,19 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   if constexpr (IVF) num_tiles = __ldg(ivf.n_work);
   else num_tiles = (n_rows + kTileRows - 1) / kTileRows;
 
-  // Flat scans walk the tiles in a multiplicative permutation of the row order (perm_mul coprime to num_tiles):
-  // at any moment the CTAs sample the whole shard, so a corpus whose scores drift along the row order (rows appended
-  // in narrative order, planted neighbours in the tail) looks like a random one to the selector.  HBM does not care:
-  // a tile is 256 KB of contiguous rows either way.
+  // Flat scans walk GROUPS of 2^perm_shift consecutive tiles in a multiplicative permutation of the row order
+  // (perm_mul coprime to the number of whole groups; a ragged tail keeps its place): at any moment the CTAs sample the
+  // whole shard, so a corpus whose scores drift along the row order (rows appended in narrative order, planted
+  // neighbours in the tail) looks like a random one to the selector.  Neighbouring CTAs still stream neighbouring
+  // tiles of one group (2 MB at shift 3 = one page of address translation), which is what HBM and the TLBs like.
+  const int perm_groups = perm_mul ? (num_tiles >> perm_shift) : 0;
   auto tile_of = [&](int j) -> int {
     if constexpr (IVF) return j;
-    else return int((uint64_t(uint32_t(j)) * perm_mul) % uint32_t(num_tiles));
+    else {
+      const int g = j >> perm_shift;
+      if (g >= perm_groups) return j;
+      return (int((uint64_t(uint32_t(g)) * perm_mul) % uint32_t(perm_groups)) << perm_shift) + (j & ((1 << perm_shift) - 1));
+    }
   };
 
   // ------------------------------------------------------------ one-time setup
@@ -807,9 +813,10 @@ struct SearchPlan {
   size_t pool_bytes;    // pooled-floor table of one 32-query pass (0 when the grid exceeds kPoolMaxCtas)
 };
 
-// multiplier of the tile permutation j -> (j * P) mod num_tiles: near num_tiles / golden ratio, coprime to num_tiles
+// multiplier of the group permutation g -> (g * P) mod n_groups: near n_groups / golden ratio, coprime to n_groups
+// (0 = identity / permutation off)
 uint32_t perm_multiplier(int64_t num_tiles) {
-  if (num_tiles < 4) return 1u;
+  if (num_tiles < 4) return 0u;
   auto gcd = [](uint64_t a, uint64_t b) { while (b) { const uint64_t t = a % b; a = b; b = t; } return a; };
   uint64_t p = (uint64_t(double(num_tiles) * 0.6180339887498949) | 1ull);
   while (gcd(p, uint64_t(num_tiles)) != 1) p += 2;
@@ -826,8 +833,9 @@ SearchPlan plan_search(int k) {
   return p;
 }
 
-// cudaFuncSetAttribute once per kernel and device instead of on every launch
-template <class Kern>
+// cudaFuncSetAttribute once per kernel and device instead of on every launch.  `Tag` makes the cache unique per
+// kernel instantiation (the kernels share one function-pointer TYPE, so the pointer type alone would alias them).
+template <class Tag, class Kern>
 int ensure_smem_attr(Kern kern, size_t smem) {
   static size_t done[64] = {0};
   int dev = 0;
@@ -838,18 +846,19 @@ int ensure_smem_attr(Kern kern, size_t smem) {
   }
   return CRAG_OK;
 }
+template <int KLIST, int CAP, int STAGES, bool IVF, bool SCORES> struct KernelTag {};
 
 template <int KLIST, int CAP, int STAGES>
 int launch_search(const CUtensorMap& tm_corpus, const CUtensorMap& tm_q, int n_rows, int num_kb, int nq, int k,
-                  int grid, const uint64_t* after_keys, uint32_t* pool, uint32_t perm_mul, uint64_t* part_keys,
-                  float* part_minmax, cudaStream_t stream) {
+                  int grid, const uint64_t* after_keys, uint32_t* pool, uint32_t perm_mul, int perm_shift,
+                  uint64_t* part_keys, float* part_minmax, cudaStream_t stream) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   const size_t smem = L::smem_bytes(num_kb);
   auto kern = search_topk_kernel<KLIST, CAP, STAGES>;
-  int rc = ensure_smem_attr(kern, smem);
+  int rc = ensure_smem_attr<KernelTag<KLIST, CAP, STAGES, false, false>>(kern, smem);
   if (rc != CRAG_OK) return rc;
   kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, n_rows, num_kb, nq, k, after_keys, pool, perm_mul,
-                                               part_keys, part_minmax, NoIvfArgs{});
+                                               perm_shift, part_keys, part_minmax, NoIvfArgs{});
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }
@@ -860,9 +869,9 @@ int launch_ivf_scan(const CUtensorMap& tm_res, const CUtensorMap& tm_q, int num_
   using L = SearchLayout<KLIST, CAP, STAGES>;
   const size_t smem = L::smem_bytes(num_kb);
   auto kern = search_topk_kernel<KLIST, CAP, STAGES, true>;
-  int rc = ensure_smem_attr(kern, smem);
+  int rc = ensure_smem_attr<KernelTag<KLIST, CAP, STAGES, true, false>>(kern, smem);
   if (rc != CRAG_OK) return rc;
-  kern<<<grid, kSearchThreads, smem, stream>>>(tm_res, tm_q, 0, num_kb, nq, k, nullptr, pool, 1u, part_keys, part_minmax, ivf);
+  kern<<<grid, kSearchThreads, smem, stream>>>(tm_res, tm_q, 0, num_kb, nq, k, nullptr, pool, 0u, 0, part_keys, part_minmax, ivf);
   CRAG_CUDA_OK(cudaGetLastError());
   return CRAG_OK;
 }
@@ -921,9 +930,14 @@ int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_st
   rc = make_tmap_bf16_2d(&tm_q, queries, uint64_t(nq), uint64_t(dim), uint64_t(dim) * 2, kNQ);
   if (rc != CRAG_OK) return rc;
   const int num_kb = dim / kBlockK;
-  const uint32_t perm = perm_multiplier(num_tiles);
-  if (k <= 64) return launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, pool, perm, part_keys, part_minmax, stream);
-  return launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, pool, perm, part_keys, part_minmax, stream);
+  // A/B switches for measurements (read once): CRAG_SEARCH_PERM_SHIFT = -1 (natural order) | 0..6, CRAG_SEARCH_POOL = 0
+  static const int env_shift = [] { const char* e = getenv("CRAG_SEARCH_PERM_SHIFT"); return e ? atoi(e) : 3; }();
+  static const bool env_pool = [] { const char* e = getenv("CRAG_SEARCH_POOL"); return e ? atoi(e) != 0 : true; }();
+  if (!env_pool) pool = nullptr;
+  const int shift = env_shift < 0 ? 0 : (env_shift > 6 ? 6 : env_shift);
+  const uint32_t perm = env_shift < 0 ? 0u : perm_multiplier(num_tiles >> shift);
+  if (k <= 64) return launch_search<64, 64, 7>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, pool, perm, shift, part_keys, part_minmax, stream);
+  return launch_search<128, 128, 5>(tm_corpus, tm_q, int(n_rows), num_kb, nq, k, grid, after_keys, pool, perm, shift, part_keys, part_minmax, stream);
 }
 
 // merge the per-CTA partials of one pass into the final (ids, scores, minmax) of its <= 32 queries
@@ -1166,7 +1180,7 @@ extern "C" int crag_search_scores(const void* corpus, int64_t n_rows, int dim, i
   using L = SearchLayout<16, 16, 9>;
   auto kern = search_topk_kernel<16, 16, 9, false, true>;
   const size_t smem = L::smem_bytes(num_kb);
-  rc = ensure_smem_attr(kern, smem);
+  rc = ensure_smem_attr<KernelTag<16, 16, 9, false, true>>(kern, smem);
   if (rc != CRAG_OK) return rc;
   for (int q0 = 0; q0 < nq; q0 += kNQ) {
     const int nqc = (nq - q0) < kNQ ? (nq - q0) : kNQ;
@@ -1174,7 +1188,7 @@ extern "C" int crag_search_scores(const void* corpus, int64_t n_rows, int dim, i
     rc = make_tmap_bf16_2d(&tm_q, static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2, uint64_t(nqc), uint64_t(dim), uint64_t(dim) * 2, kNQ);
     if (rc != CRAG_OK) return rc;
     ScoreArgs sa{out_scores + int64_t(q0) * out_ld, out_ld};
-    kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, int(n_rows), num_kb, nqc, 1, nullptr, nullptr, 1u, nullptr,
+    kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, int(n_rows), num_kb, nqc, 1, nullptr, nullptr, 0u, 0, nullptr,
                                                  part_minmax, sa);
     CRAG_CUDA_OK(cudaGetLastError());
     if (out_minmax) {

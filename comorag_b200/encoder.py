@@ -287,7 +287,7 @@ class BertEncoderB200:
 
 
 _GRAPH_MAX_SEQS = 32
-_GRAPH_BUCKETS = (128, 512, 2048)      # packed-token buckets served by captured graphs
+_GRAPH_BUCKETS = (128, 256, 512, 768, 1024, 1536, 2048)      # packed-token buckets served by captured graphs
 
 
 class _EncoderGraph:

@@ -20,10 +20,12 @@ from typing import Dict
 
 
 def install(package: str = "src.comorag", rerank: bool = False, summaries: bool = True, search: bool = True,
-            knn: bool = True) -> Dict[str, int]:
+            knn: bool = True, encoder: bool = True) -> Dict[str, int]:
     """Returns {name: number of module attributes (or class methods) rebound}.  `rerank=True` also swaps the LLM
     filter for the dense reranker (new arithmetic, off by default so answers stay reference-identical); `search`
-    rebinds the four ComoRAG retrieval methods, `knn` the synonymy-edge retrieve_knn."""
+    rebinds the four ComoRAG retrieval methods, `knn` the synonymy-edge retrieve_knn; `encoder=False` keeps the
+    reference's own embedding model class (HF, fp32) and swaps only the store / search half -- the parity tests use
+    that to compare rankings without the bf16 encoder's error in the way."""
     from . import embedding_model as em
     from . import embedding_store as es
     from . import rerank as rr
@@ -31,11 +33,10 @@ def install(package: str = "src.comorag", rerank: bool = False, summaries: bool 
 
     ref_em = importlib.import_module(package + ".embedding_model")
     ref_es = importlib.import_module(package + ".embedding_store")
-    swaps = {
-        "_get_embedding_model_class": (ref_em._get_embedding_model_class, em._get_embedding_model_class),
-        "BGEEmbeddingModel": (ref_em.BGEEmbeddingModel, em.BGEEmbeddingModel),
-        "EmbeddingStore": (ref_es.EmbeddingStore, es.EmbeddingStore),
-    }
+    swaps = {"EmbeddingStore": (ref_es.EmbeddingStore, es.EmbeddingStore)}
+    if encoder:
+        swaps["_get_embedding_model_class"] = (ref_em._get_embedding_model_class, em._get_embedding_model_class)
+        swaps["BGEEmbeddingModel"] = (ref_em.BGEEmbeddingModel, em.BGEEmbeddingModel)
     if summaries:
         ref_eu = importlib.import_module(package + ".utils.embed_utils")
         swaps["get_similar_summaries"] = (ref_eu.get_similar_summaries, rt.get_similar_summaries)

@@ -69,17 +69,14 @@ def test_reference_arm_reproduces_the_committed_trace():
     # run-to-run the reference moves by ~3e-5 in normalised score (fp32 padding-batch effects: a text's batch
     # companions depend on thread completion order), nothing more
     summary = H.compare_traces(gold, out, score_tol=5e-4)
+    assert not summary["problems"], summary["problems"]
     assert summary["queries"] == len(gold["trace"]) == 12
     # the char-iteration bug (ComoRAG.py:470, 909-935): each tri_retrieve encodes len(query) single characters twice
     assert out["query_encodes"]["encoded_texts"] > 20 * len(out["trace"])
 
 
-@needs_ref
-@pytest.mark.gpu
-def test_unmodified_comorag_runs_on_the_shim_and_retrieves_what_the_reference_retrieves():
-    import torch
+def _count_device_calls():
     from comorag_b200 import index as crag_index
-    ref = reference_arm()
     calls = {"scores": 0, "rank": 0, "topk": 0}
     real = (crag_index.DenseIndex.scores_device, crag_index.DenseIndex.rank_device, crag_index.DenseIndex.search_device)
 
@@ -91,24 +88,72 @@ def test_unmodified_comorag_runs_on_the_shim_and_retrieves_what_the_reference_re
     crag_index.DenseIndex.scores_device = counting("scores", real[0])
     crag_index.DenseIndex.rank_device = counting("rank", real[1])
     crag_index.DenseIndex.search_device = counting("topk", real[2])
+
+    def restore():
+        (crag_index.DenseIndex.scores_device, crag_index.DenseIndex.rank_device, crag_index.DenseIndex.search_device) = real
+    return calls, restore
+
+
+def _report(name, payload):
+    out = os.path.join(os.path.dirname(HERE), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, name), "w") as f:
+        json.dump(payload, f, indent=1)
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_unmodified_comorag_search_half_on_the_device_matches_the_reference_rankings():
+    """install(encoder=False): the reference's own fp32 encoder feeds OUR stores, and unmodified ComoRAG.py runs its
+    fact / passage / summary / timeline searches and the synonymy kNN on the device kernels.  Only the bf16 storage
+    of rows and queries separates the two arms, so every ranking must agree to 5e-3 in normalised score."""
+    ref = reference_arm()
+    calls, restore = _count_device_calls()
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            got = H.run_cinderella("shim_search", tmp, REF_ROOT)
+    finally:
+        restore()
+        import comorag_b200.install as crag
+        crag.uninstall_search("src.comorag")
+    summary = H.compare_traces(ref, got, score_tol=5e-3)
+    _report("e2e_search_half.json", {"summary": summary, "device_calls": calls})
+    assert not summary["problems"], summary["problems"]
+    n = len(ref["trace"])
+    assert summary["queries"] == n >= 9
+    assert calls["scores"] >= 3 * n and calls["rank"] >= 2 * n and calls["topk"] >= n
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_unmodified_comorag_runs_on_the_shim_and_retrieves_what_the_reference_retrieves():
+    import torch
+    ref = reference_arm()
+    calls, restore = _count_device_calls()
     try:
         with tempfile.TemporaryDirectory() as tmp:
             got = H.run_cinderella("shim", tmp, REF_ROOT)
     finally:
-        (crag_index.DenseIndex.scores_device, crag_index.DenseIndex.rank_device, crag_index.DenseIndex.search_device) = real
+        restore()
     main = sys.modules["src.comorag.ComoRAG"]
     assert main.ComoRAG.get_fact_scores.__module__ == "comorag_b200.comorag_methods"
     assert main.EmbeddingStore.__module__ == "comorag_b200.embedding_store"
-    summary = H.compare_traces(ref, got)
+    # the GPU encoder is bf16 against the reference's fp32 HF model, and this 2-layer synthetic checkpoint is badly
+    # conditioned (weights N(0, 0.08)): embedding max-abs error up to 1e-2 moves min-max-normalised scores by up to
+    # a few 1e-2 .. 1e-1.  Rankings must still be consistent within twice the measured deviation of each query.
+    summary = H.compare_traces(ref, got, score_tol=0.25)
     n = len(ref["trace"])
+    _report("e2e_full_shim.json", {"summary": summary, "device_calls": calls, "query_encodes": got["query_encodes"],
+                                   "reference_query_encodes": ref["query_encodes"]})
+    assert not summary["problems"], summary["problems"]
     assert summary["queries"] == n >= 9
     # every tri_retrieve ran on the device kernels: 1 fact score-all pass, >= 2 score-all + rank passes (passages,
     # summaries), 1 fused top-k (timeline summaries); retrieve_knn added fused top-k passes at index time
     assert calls["scores"] >= 3 * n and calls["rank"] >= 2 * n and calls["topk"] >= n
-    # and the per-character encode waste is gone: one encoded text per tri_retrieve instead of 2 * len(query) + 4
+    # and the per-character encode waste is gone: a couple of encoded texts per tri_retrieve instead of 2 * len(query) + 4
     assert got["query_encodes"]["encoded_texts"] <= 2 * n + 16 * 3
     assert ref["query_encodes"]["encoded_texts"] > 5 * got["query_encodes"]["encoded_texts"]
     # the golden trace committed from the build container agrees with the shim as well
     gold = json.load(open(GOLDEN))
-    H.compare_traces(gold, got)
+    assert not H.compare_traces(gold, got, score_tol=0.25)["problems"]
     torch.cuda.synchronize()
