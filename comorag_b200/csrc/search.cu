@@ -36,38 +36,66 @@ constexpr int kEpiThreads = 128;
 constexpr int kAccStages = 16;       // score-tile buffers in TMEM: the scan may run 16 tiles ahead of the select warps
 constexpr uint32_t kTmemCols = kAccStages * kNQ;  // 512 columns = all of TMEM (1 CTA per SM)
 
-// Pooled admission floor.  Every CTA publishes the scores of its current best kPoolM rows per query (after each
-// flush of that query's candidate buffer) in pool[q][cta][kPoolM] (orderable u32, 0 = nothing yet).  Published values
-// are scores of distinct rows of THIS shard (one CTA's j-th best only ever improves, so values read at different
-// times still have distinct rows at least that good), hence the k-th largest of the pooled values is a score that
-// at least k shard rows reach: nothing below it can rank in the top-k.  Each CTA recomputes that k-th value from
-// time to time (tiles 1, 2, 4, 8, ... and every 32nd) and raises its admission thresholds to it, so all CTAs work
-// with (almost) the global k-th best seen so far instead of their private one -- this replaces the separate sample
-// pre-pass of round 1 (two extra launches) and cuts admissions at k = 100 by about two orders of magnitude.
+// Pooled admission floor.  Every CTA publishes its current best kPoolM KEYS per query (after each flush of that
+// query's candidate buffer) in pool[q][cta][kPoolM] (packed u64 keys, 0 = nothing yet).  Published keys belong to
+// distinct rows of THIS shard (one CTA's j-th best key only ever improves, so values read at different times still
+// stand for distinct rows at least that good), hence the k-th largest pooled key is a key that at least k shard rows
+// reach: no row with a smaller key can rank in the top-k.  Each CTA recomputes that k-th key from time to time
+// (after tiles 2, 8, 32 and every 64th) and raises its admission thresholds to it, so all CTAs work with
+// (almost) the global k-th best seen so far instead of their private one.  This replaces the separate sample
+// pre-pass of round 1 (two launches fewer), cuts admissions at k = 100 by about two orders of magnitude, and --
+// because the floor is a full key, row id included -- keeps tie-heavy corpora (duplicate rows) from flooding the
+// selector with rows that only tie the k-th score.
 constexpr int kPoolM = 4;
-constexpr int kPoolMaxCtas = 160;   // 5 uint4 per lane
+constexpr int kPoolMaxCtas = 160;   // 5 entries (2 x uint4 each) per lane
+constexpr int kPoolVals = (kPoolMaxCtas / 32) * kPoolM;
 
-__device__ __forceinline__ float pooled_floor(const uint32_t* __restrict__ pool_q, int n_ctas, int k, int lane) {
-  uint32_t v[(kPoolMaxCtas / 32) * kPoolM];
+__device__ __forceinline__ uint64_t pooled_floor_key(const uint64_t* __restrict__ pool_q, int n_ctas, int k, int lane) {
+  uint32_t hi[kPoolVals], lo[kPoolVals];
 #pragma unroll
   for (int i = 0; i < kPoolMaxCtas / 32; ++i) {
     const int c = lane + 32 * i;
-    uint4 x = make_uint4(0u, 0u, 0u, 0u);
-    if (c < n_ctas) x = __ldcg(reinterpret_cast<const uint4*>(pool_q) + c);   // L2: other SMs keep updating it
-    v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+    uint4 x = make_uint4(0u, 0u, 0u, 0u), y = make_uint4(0u, 0u, 0u, 0u);
+    if (c < n_ctas) {   // L2: other SMs keep updating it
+      x = __ldcg(reinterpret_cast<const uint4*>(pool_q) + 2 * c);
+      y = __ldcg(reinterpret_cast<const uint4*>(pool_q) + 2 * c + 1);
+    }
+    lo[4 * i + 0] = x.x; hi[4 * i + 0] = x.y; lo[4 * i + 1] = x.z; hi[4 * i + 1] = x.w;
+    lo[4 * i + 2] = y.x; hi[4 * i + 2] = y.y; lo[4 * i + 3] = y.z; hi[4 * i + 3] = y.w;
   }
-  // largest T (low 8 bits clear) with count(v >= T) >= k, by bisection on the orderable bits
+  // largest T with count(hi >= T) >= k, by bisection on the orderable score bits
   uint32_t t = 0;
 #pragma unroll 1
-  for (int bit = 31; bit >= 8; --bit) {
+  for (int bit = 31; bit >= 0; --bit) {
     const uint32_t cand = t | (1u << bit);
     int c = 0;
 #pragma unroll
-    for (int i = 0; i < (kPoolMaxCtas / 32) * kPoolM; ++i) c += (v[i] >= cand) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= k) t = cand;
+    for (int i = 0; i < kPoolVals; ++i) c += (hi[i] >= cand) ? 1 : 0;
+    if (__reduce_add_sync(0xffffffffu, c) >= k) t = cand;
   }
-  return t ? unorderable_f32(t) : -INFINITY;   // clearing low bits only lowers the value: still a valid floor
+  if (t == 0) return 0ull;   // fewer than k rows published so far
+  int c_gt = 0, c_eq = 0;
+  uint32_t lo_min = 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 0; i < kPoolVals; ++i) {
+    c_gt += (hi[i] > t) ? 1 : 0;
+    if (hi[i] == t) { ++c_eq; lo_min = lo[i] < lo_min ? lo[i] : lo_min; }
+  }
+  c_gt = __reduce_add_sync(0xffffffffu, c_gt);
+  c_eq = __reduce_add_sync(0xffffffffu, c_eq);
+  const int need = k - c_gt;             // rank wanted among the keys that share the k-th score (>= 1, <= c_eq)
+  if (need >= c_eq) return (uint64_t(t) << 32) | __reduce_min_sync(0xffffffffu, lo_min);   // the usual case: no tie
+  // ties at the k-th score (duplicate rows): the need-th largest low word (= need-th smallest row id) among them
+  uint32_t l = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = l | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < kPoolVals; ++i) c += (hi[i] == t && lo[i] >= cand) ? 1 : 0;
+    if (__reduce_add_sync(0xffffffffu, c) >= need) l = cand;
+  }
+  return (uint64_t(t) << 32) | l;
 }
 
 template <int KLIST, int CAP, int STAGES>
@@ -80,7 +108,7 @@ struct SearchLayout {
            + kNQ * 4               // thr_f
            + kNQ * 4               // cnt
            + kNQ * 8 + kNQ * 4     // continuation bound (key, score)
-           + kNQ * 4               // admission floor
+           + kNQ * 8               // pooled admission floor (key)
            + 4 * kNQ * 2 * 4       // min/max cross-warp reduction
            + 16;                   // tmem base
   }
@@ -118,7 +146,7 @@ template <int KLIST, int CAP, int STAGES, bool IVF = false, bool SCORES = false>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_constant__ CUtensorMap tm_q,
                    int n_rows, int num_kb, int nq, int k, const uint64_t* __restrict__ after_keys,
-                   uint32_t* __restrict__ pool, uint32_t perm_mul, int perm_shift, uint64_t* __restrict__ part_keys,
+                   uint64_t* __restrict__ pool, uint32_t perm_mul, int perm_shift, uint64_t* __restrict__ part_keys,
                    float* __restrict__ part_minmax, const typename IvfParam<IVF, SCORES>::type ivf) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -138,8 +166,8 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   float* red = reinterpret_cast<float*>(cnt + kNQ);        // [4][kNQ][2]
   uint64_t* bnd_key = reinterpret_cast<uint64_t*>(red + 4 * kNQ * 2);  // [kNQ] admit only keys < bnd_key
   float* bnd_f = reinterpret_cast<float*>(bnd_key + kNQ);              // [kNQ] score part of the bound
-  float* floor_f = bnd_f + kNQ;                                        // [kNQ] pooled admission floor
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(floor_f + kNQ);
+  uint64_t* floor_key = reinterpret_cast<uint64_t*>(bnd_f + kNQ);      // [kNQ] pooled admission floor (see pooled_floor_key)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(floor_key + kNQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -185,8 +213,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   for (int i = threadIdx.x; i < kNQ * L::kKeysPerQuery; i += kSearchThreads) keys[i] = 0ull;
   if (threadIdx.x < kNQ) {
     thr_key[threadIdx.x] = 0ull;
-    // floor_f: a score at least k rows of THIS shard are known to reach (pooled over all CTAs, see pooled_floor)
-    floor_f[threadIdx.x] = -INFINITY;
+    floor_key[threadIdx.x] = 0ull;
     thr_f[threadIdx.x] = -INFINITY;
     cnt[threadIdx.x] = 0;
     // "search after": rank continuation for k > 128 -- only candidates strictly below the previous pass's last key
@@ -265,28 +292,39 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
     auto publish = [&](int q) {
       if (pool != nullptr && lane < kPoolM) {
         const uint64_t kk = keys[q * L::kKeysPerQuery + lane];
-        if (kk) pool[(size_t(q) * gridDim.x + blockIdx.x) * kPoolM + lane] = uint32_t(kk >> 32);
+        if (kk) pool[(size_t(q) * gridDim.x + blockIdx.x) * kPoolM + lane] = kk;
       }
     };
     // raise the owned queries' thresholds to the pooled floor
     auto refresh = [&]() {
       if (pool == nullptr) return;
       for (int q = ew; q < nq; q += 4) {
-        const float pf = pooled_floor(pool + size_t(q) * gridDim.x * kPoolM, int(gridDim.x), k, lane);
-        if (lane == 0 && pf > floor_f[q]) {
-          floor_f[q] = pf;
-          thr_f[q] = fmaxf(thr_f[q], pf);
+        const uint64_t pf = pooled_floor_key(pool + size_t(q) * gridDim.x * kPoolM, int(gridDim.x), k, lane);
+        if (lane == 0 && pf > floor_key[q]) {
+          floor_key[q] = pf;
+          if (pf > thr_key[q]) {
+            thr_key[q] = pf;
+            thr_f[q] = key_score(pf);
+          }
         }
       }
+    };
+    // after a flush of query q (lane 0 of the owning warp): threshold = max(local k-th key, pooled floor)
+    auto settle = [&](int q) {
+      uint64_t t = thr_key[q];
+      if (floor_key[q] > t) { t = floor_key[q]; thr_key[q] = t; }
+      thr_f[q] = t ? key_score(t) : -INFINITY;
     };
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
     for (int j = blockIdx.x; j < num_tiles; j += gridDim.x, ++it) {
       const int tile = tile_of(j);
-      // tiles 1, 2, 4, 8, ... and every 32nd: all four warps take the same branch (it is CTA-uniform); the smem
-      // thresholds they update are read again only after the next named barrier
-      if (it > 0 && ((it & (it - 1)) == 0 || (it & 31) == 0)) {
+      // after tiles 2, 8, 32 and every 64th: all four warps take the same branch (it is CTA-uniform); the smem
+      // thresholds they update are read again only after the next named barrier.  (After two tiles per CTA the pool
+      // already holds the best of ~38k rows; what is admitted later is k * ln(rows / 38k) keys per query over ALL
+      // CTAs, so further refreshes are for long scans and drifting corpora only.)
+      if (it == 2 || it == 8 || it == 32 || (it >= 64 && (it & 63) == 0)) {
         refresh();
         named_bar_sync(1, kEpiThreads);
       }
@@ -361,10 +399,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
         named_bar_sync(1, kEpiThreads);
         for (int q = ew; q < kNQ; q += 4) {
           flush_query<KLIST, CAP>(keys + q * L::kKeysPerQuery, 128 - KLIST, k, &thr_key[q], lane);
-          if (lane == 0) {
-            const uint64_t t = thr_key[q];
-            thr_f[q] = fmaxf(floor_f[q], t ? key_score(t) : -INFINITY);
-          }
+          if (lane == 0) settle(q);
           publish(q);
         }
         named_bar_sync(1, kEpiThreads);
@@ -390,8 +425,7 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
           if (c >= CAP) {
             flush_query<KLIST, CAP>(keys + q * L::kKeysPerQuery, CAP, k, &thr_key[q], lane);
             if (lane == 0) {
-              const uint64_t t = thr_key[q];
-              thr_f[q] = fmaxf(floor_f[q], t ? key_score(t) : -INFINITY);
+              settle(q);
               cnt[q] = 0;
             }
             publish(q);
@@ -413,7 +447,8 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
     if constexpr (!SCORES) {
       for (int q = ew; q < kNQ; q += 4) {
         const int c = min(cnt[q], CAP);
-        if (c > 0) flush_query<KLIST, CAP>(keys + q * L::kKeysPerQuery, c, k, &thr_key[q], lane);
+        if (c > kInsertMax) flush_query<KLIST, CAP>(keys + q * L::kKeysPerQuery, c, k, &thr_key[q], lane);
+        else if (c > 0) insert_few<KLIST, CAP>(keys + q * L::kKeysPerQuery, c, k, &thr_key[q], lane);
         __syncwarp();
         uint64_t* dst = part_keys + (size_t(blockIdx.x) * kNQ + q) * k;
         for (int j = lane; j < k; j += 32) dst[j] = keys[q * L::kKeysPerQuery + j];
@@ -829,7 +864,7 @@ SearchPlan plan_search(int k) {
   if (p.grid <= 0) p.grid = 148;
   p.keys_bytes = ((size_t(p.grid) * kNQ * k * 8) + 255) & ~size_t(255);
   p.minmax_bytes = ((size_t(p.grid) * kNQ * 2 * 4) + 255) & ~size_t(255);
-  p.pool_bytes = p.grid <= kPoolMaxCtas ? ((size_t(kNQ) * p.grid * kPoolM * 4 + 255) & ~size_t(255)) : 0;
+  p.pool_bytes = p.grid <= kPoolMaxCtas ? ((size_t(kNQ) * p.grid * kPoolM * 8 + 255) & ~size_t(255)) : 0;
   return p;
 }
 
@@ -850,7 +885,7 @@ template <int KLIST, int CAP, int STAGES, bool IVF, bool SCORES> struct KernelTa
 
 template <int KLIST, int CAP, int STAGES>
 int launch_search(const CUtensorMap& tm_corpus, const CUtensorMap& tm_q, int n_rows, int num_kb, int nq, int k,
-                  int grid, const uint64_t* after_keys, uint32_t* pool, uint32_t perm_mul, int perm_shift,
+                  int grid, const uint64_t* after_keys, uint64_t* pool, uint32_t perm_mul, int perm_shift,
                   uint64_t* part_keys, float* part_minmax, cudaStream_t stream) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   const size_t smem = L::smem_bytes(num_kb);
@@ -865,7 +900,7 @@ int launch_search(const CUtensorMap& tm_corpus, const CUtensorMap& tm_q, int n_r
 
 template <int KLIST, int CAP, int STAGES>
 int launch_ivf_scan(const CUtensorMap& tm_res, const CUtensorMap& tm_q, int num_kb, int nq, int k, int grid,
-                    uint32_t* pool, uint64_t* part_keys, float* part_minmax, const IvfArgs& ivf, cudaStream_t stream) {
+                    uint64_t* pool, uint64_t* part_keys, float* part_minmax, const IvfArgs& ivf, cudaStream_t stream) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
   const size_t smem = L::smem_bytes(num_kb);
   auto kern = search_topk_kernel<KLIST, CAP, STAGES, true>;
@@ -918,10 +953,10 @@ int scan_pass(const void* corpus, int64_t n_rows, int dim, int64_t corpus_row_st
   uint64_t* part_keys = static_cast<uint64_t*>(workspace);
   float* part_minmax = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes);
   // pooled floor: needs its table in the workspace and pays off once a CTA sees more than a couple of tiles
-  uint32_t* pool = nullptr;
+  uint64_t* pool = nullptr;
   const int64_t num_tiles = (n_rows + kTileRows - 1) / kTileRows;
   if (plan.pool_bytes && workspace_bytes >= plan.keys_bytes + plan.minmax_bytes + plan.pool_bytes && num_tiles >= 4 * int64_t(grid)) {
-    pool = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes + plan.minmax_bytes);
+    pool = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes + plan.minmax_bytes);
     CRAG_CUDA_OK(cudaMemsetAsync(pool, 0, plan.pool_bytes, stream));
   }
   CUtensorMap tm_corpus, tm_q;
@@ -1024,9 +1059,9 @@ extern "C" int crag_ivf_search(const void* residuals, int64_t n_rows_padded, int
                                             const_cast<float*>(ivf.coarse), const_cast<int4*>(ivf.work), const_cast<int*>(ivf.n_work));
     CRAG_CUDA_OK(cudaGetLastError());
     // every CTA of the grid publishes a (possibly empty) partial list, so the merge always reads sp.grid parts
-    uint32_t* pool = nullptr;
+    uint64_t* pool = nullptr;
     if (sp.pool_bytes) {
-      pool = reinterpret_cast<uint32_t*>(ws + ip.pool_off);
+      pool = reinterpret_cast<uint64_t*>(ws + ip.pool_off);
       CRAG_CUDA_OK(cudaMemsetAsync(pool, 0, sp.pool_bytes, stream));
     }
     rc = (k <= 64) ? launch_ivf_scan<64, 64, 7>(tm_res, tm_q, num_kb, nqc, k, sp.grid, pool, part_keys, part_minmax, ivf, stream)

@@ -103,4 +103,36 @@ __device__ __forceinline__ void flush_query(uint64_t* qkeys, int c, int k, uint6
   __syncwarp();
 }
 
+// Cheap flush for a handful of buffered candidates (c <= kInsertMax): each one is placed into the sorted list by a
+// warp-parallel shift instead of re-sorting KLIST + CAP keys.  With the pooled admission floor a CTA ends its scan
+// with 0-3 candidates pending per query, and 32 full bitonic sorts at the tail of a short scan (multi-GPU strong
+// scaling: ~66 tiles per CTA) cost more than the candidates are worth.
+constexpr int kInsertMax = 8;
+template <int KLIST, int CAP>
+__device__ __forceinline__ void insert_few(uint64_t* qkeys, int c, int k, uint64_t* thr_key, int lane) {
+  constexpr int E = KLIST / 32;
+  static_assert(KLIST % 32 == 0, "KLIST must be a multiple of 32");
+  for (int i = 0; i < c; ++i) {
+    const uint64_t cand = qkeys[KLIST + i];
+    uint64_t nv[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int g = lane * E + j;
+      const uint64_t cur = qkeys[g];
+      const uint64_t prev = g > 0 ? qkeys[g - 1] : ~0ull;
+      // descending list: keys above the candidate stay, the first slot not above it takes it, the rest shift down
+      nv[j] = cur > cand ? cur : (prev > cand ? cand : prev);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int g = lane * E + j;
+      qkeys[g] = g < k ? nv[j] : 0ull;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) *thr_key = qkeys[k - 1];
+  __syncwarp();
+}
+
 }  // namespace crag

@@ -328,10 +328,10 @@ def run_cinderella(arm: str, workdir: str, ref_root: str, max_loops: int = 1, qu
     if arm != "shim":
         # `accelerate` is absent: drop device_map from the HF init params (shim 2)
         if not getattr(ref_bge.BGEEmbeddingModel, "_harness_patched", False):
-            orig = ref_bge.BGEEmbeddingModel._init_embedding_config
+            _orig_init = ref_bge.BGEEmbeddingModel._init_embedding_config
 
-            def _init(self):
-                orig(self)
+            def _init(self, _orig_init=_orig_init):
+                _orig_init(self)
                 self.embedding_config.model_init_params.pop("device_map", None)
             ref_bge.BGEEmbeddingModel._init_embedding_config = _init
             ref_bge.BGEEmbeddingModel._harness_patched = True
@@ -412,8 +412,8 @@ def run_cinderella(arm: str, workdir: str, ref_root: str, max_loops: int = 1, qu
             }
             n_edges = rag.graph.ecount()
     finally:
-        for name, orig in wrapped.items():
-            setattr(cls, name, orig)
+        for name, original in wrapped.items():
+            setattr(cls, name, original)
         main.get_similar_summaries = orig_gss
     return {"arm": arm, "trace": trace, "answers": [getattr(s, "answer", None) for s in solutions], "stores": stores,
             "graph_edges": n_edges, "index_encodes": index_encodes,
@@ -461,6 +461,9 @@ def compare_traces(ref: Dict, got: Dict, score_tol: float = 0.08) -> Dict:
                 problems.append(f"{query!r} {kind}: different item sets")
                 continue
             dev = max(dev, max((abs(rs[i] - gs[i]) for i in rs), default=0.0))
+        re_, ge_ = dict(zip(r["epi"]["texts"], r["epi"]["scores"])), dict(zip(g["epi"]["texts"], g["epi"]["scores"]))
+        if set(re_) == set(ge_):
+            dev = max(dev, max((abs(re_[i] - ge_[i]) for i in re_), default=0.0))
         if dev > score_tol:
             problems.append(f"{query!r}: normalised scores differ by {dev:.4f} > {score_tol}")
         worst = max(worst, dev)
