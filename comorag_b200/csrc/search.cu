@@ -41,43 +41,38 @@ constexpr uint32_t kTmemCols = kAccStages * kNQ;  // 512 columns = all of TMEM (
 // distinct rows of THIS shard (one CTA's j-th best key only ever improves, so values read at different times still
 // stand for distinct rows at least that good), hence the k-th largest pooled key is a key that at least k shard rows
 // reach: no row with a smaller key can rank in the top-k.  Each CTA recomputes that k-th key from time to time
-// (after tiles 2, 8, 32 and every 64th) and raises its admission thresholds to it, so all CTAs work with
+// (after tiles 2, 12, 48 and every 128th) and raises its admission thresholds to it, so all CTAs work with
 // (almost) the global k-th best seen so far instead of their private one.  This replaces the separate sample
 // pre-pass of round 1 (two launches fewer), cuts admissions at k = 100 by about two orders of magnitude, and --
 // because the floor is a full key, row id included -- keeps tie-heavy corpora (duplicate rows) from flooding the
 // selector with rows that only tie the k-th score.
 constexpr int kPoolM = 4;
-constexpr int kPoolMaxCtas = 160;   // 5 entries (2 x uint4 each) per lane
-constexpr int kPoolVals = (kPoolMaxCtas / 32) * kPoolM;
+constexpr int kPoolMaxCtas = 160;   // 5 entries per lane
+constexpr int kPoolSmallK = 16;     // up to this k only each CTA's BEST key is pooled (148 values decide a top-16 floor)
 
-__device__ __forceinline__ uint64_t pooled_floor_key(const uint64_t* __restrict__ pool_q, int n_ctas, int k, int lane) {
-  uint32_t hi[kPoolVals], lo[kPoolVals];
+// k-th largest of the NV keys each lane holds (hi = score word, lo = row word), 0 when fewer than k are set.
+// Bisection on the score bits, counted with four independent accumulators (the select warps run one warp per
+// scheduler, so a serial chain of NV dependent adds would cost its full latency 32 times); ties at the k-th score
+// (duplicate rows) are resolved by a second bisection on the row word, otherwise a single min-reduce finishes.
+template <int NV>
+__device__ __forceinline__ uint64_t kth_largest_key(const uint32_t (&hi)[NV], const uint32_t (&lo)[NV], int k) {
+  auto count_ge = [&](uint32_t cand) -> int {
+    int c[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int i = 0; i < kPoolMaxCtas / 32; ++i) {
-    const int c = lane + 32 * i;
-    uint4 x = make_uint4(0u, 0u, 0u, 0u), y = make_uint4(0u, 0u, 0u, 0u);
-    if (c < n_ctas) {   // L2: other SMs keep updating it
-      x = __ldcg(reinterpret_cast<const uint4*>(pool_q) + 2 * c);
-      y = __ldcg(reinterpret_cast<const uint4*>(pool_q) + 2 * c + 1);
-    }
-    lo[4 * i + 0] = x.x; hi[4 * i + 0] = x.y; lo[4 * i + 1] = x.z; hi[4 * i + 1] = x.w;
-    lo[4 * i + 2] = y.x; hi[4 * i + 2] = y.y; lo[4 * i + 3] = y.z; hi[4 * i + 3] = y.w;
-  }
-  // largest T with count(hi >= T) >= k, by bisection on the orderable score bits
+    for (int i = 0; i < NV; ++i) c[i & 3] += (hi[i] >= cand) ? 1 : 0;
+    return __reduce_add_sync(0xffffffffu, (c[0] + c[1]) + (c[2] + c[3]));
+  };
   uint32_t t = 0;
 #pragma unroll 1
   for (int bit = 31; bit >= 0; --bit) {
     const uint32_t cand = t | (1u << bit);
-    int c = 0;
-#pragma unroll
-    for (int i = 0; i < kPoolVals; ++i) c += (hi[i] >= cand) ? 1 : 0;
-    if (__reduce_add_sync(0xffffffffu, c) >= k) t = cand;
+    if (count_ge(cand) >= k) t = cand;
   }
   if (t == 0) return 0ull;   // fewer than k rows published so far
   int c_gt = 0, c_eq = 0;
   uint32_t lo_min = 0xFFFFFFFFu;
 #pragma unroll
-  for (int i = 0; i < kPoolVals; ++i) {
+  for (int i = 0; i < NV; ++i) {
     c_gt += (hi[i] > t) ? 1 : 0;
     if (hi[i] == t) { ++c_eq; lo_min = lo[i] < lo_min ? lo[i] : lo_min; }
   }
@@ -85,17 +80,44 @@ __device__ __forceinline__ uint64_t pooled_floor_key(const uint64_t* __restrict_
   c_eq = __reduce_add_sync(0xffffffffu, c_eq);
   const int need = k - c_gt;             // rank wanted among the keys that share the k-th score (>= 1, <= c_eq)
   if (need >= c_eq) return (uint64_t(t) << 32) | __reduce_min_sync(0xffffffffu, lo_min);   // the usual case: no tie
-  // ties at the k-th score (duplicate rows): the need-th largest low word (= need-th smallest row id) among them
   uint32_t l = 0;
 #pragma unroll 1
   for (int bit = 31; bit >= 0; --bit) {
     const uint32_t cand = l | (1u << bit);
     int c = 0;
 #pragma unroll
-    for (int i = 0; i < kPoolVals; ++i) c += (hi[i] == t && lo[i] >= cand) ? 1 : 0;
+    for (int i = 0; i < NV; ++i) c += (hi[i] == t && lo[i] >= cand) ? 1 : 0;
     if (__reduce_add_sync(0xffffffffu, c) >= need) l = cand;
   }
   return (uint64_t(t) << 32) | l;
+}
+
+__device__ __forceinline__ uint64_t pooled_floor_key(const uint64_t* __restrict__ pool_q, int n_ctas, int k, int lane) {
+  if (k <= kPoolSmallK) {
+    uint32_t hi[kPoolMaxCtas / 32], lo[kPoolMaxCtas / 32];
+#pragma unroll
+    for (int i = 0; i < kPoolMaxCtas / 32; ++i) {
+      const int c = lane + 32 * i;
+      const uint64_t x = c < n_ctas ? __ldcg(pool_q + size_t(c) * kPoolM) : 0ull;   // L2: other SMs keep updating it
+      lo[i] = uint32_t(x);
+      hi[i] = uint32_t(x >> 32);
+    }
+    return kth_largest_key<kPoolMaxCtas / 32>(hi, lo, k);
+  }
+  constexpr int NV = (kPoolMaxCtas / 32) * kPoolM;
+  uint32_t hi[NV], lo[NV];
+#pragma unroll
+  for (int i = 0; i < kPoolMaxCtas / 32; ++i) {
+    const int c = lane + 32 * i;
+    uint4 x = make_uint4(0u, 0u, 0u, 0u), y = make_uint4(0u, 0u, 0u, 0u);
+    if (c < n_ctas) {
+      x = __ldcg(reinterpret_cast<const uint4*>(pool_q) + 2 * c);
+      y = __ldcg(reinterpret_cast<const uint4*>(pool_q) + 2 * c + 1);
+    }
+    lo[4 * i + 0] = x.x; hi[4 * i + 0] = x.y; lo[4 * i + 1] = x.z; hi[4 * i + 1] = x.w;
+    lo[4 * i + 2] = y.x; hi[4 * i + 2] = y.y; lo[4 * i + 3] = y.z; hi[4 * i + 3] = y.w;
+  }
+  return kth_largest_key<NV>(hi, lo, k);
 }
 
 template <int KLIST, int CAP, int STAGES>
@@ -320,11 +342,11 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
     int it = 0;
     for (int j = blockIdx.x; j < num_tiles; j += gridDim.x, ++it) {
       const int tile = tile_of(j);
-      // after tiles 2, 8, 32 and every 64th: all four warps take the same branch (it is CTA-uniform); the smem
+      // after tiles 2, 12, 48 and every 128th: all four warps take the same branch (it is CTA-uniform); the smem
       // thresholds they update are read again only after the next named barrier.  (After two tiles per CTA the pool
       // already holds the best of ~38k rows; what is admitted later is k * ln(rows / 38k) keys per query over ALL
       // CTAs, so further refreshes are for long scans and drifting corpora only.)
-      if (it == 2 || it == 8 || it == 32 || (it >= 64 && (it & 63) == 0)) {
+      if (it == 2 || it == 12 || it == 48 || (it >= 128 && (it & 127) == 0)) {
         refresh();
         named_bar_sync(1, kEpiThreads);
       }

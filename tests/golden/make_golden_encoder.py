@@ -54,15 +54,23 @@ def build_checkpoint(chunks):
                      intermediate_size=256, max_position_embeddings=512, type_vocab_size=2)
     torch.manual_seed(0)
     model = BertModel(cfg)
-    # HF's default init (std 0.02) collapses all embeddings to one direction; widen it so parity is informative
+    # HF's default init (std 0.02) collapses all embeddings to one direction (any two texts: cosine > 0.98), which
+    # makes every ranking noise.  Give the WORD embeddings unit scale and keep the position / layer weights small:
+    # the residual stream is then dominated by what the text says, document-document cosines spread over 0.6-0.9
+    # and query-document raw score ranges are 0.1-0.3 -- rankings that the end-to-end parity test can actually hold
+    # an implementation to (tests/test_e2e_cinderella.py).
     with torch.no_grad():
         for n, p in model.named_parameters():
-            if p.dim() == 2:
-                p.normal_(0.0, 0.08)
+            if "word_embeddings" in n:
+                p.normal_(0.0, 1.0)
+            elif "position_embeddings" in n or "token_type_embeddings" in n:
+                p.normal_(0.0, 0.02)
+            elif p.dim() == 2:
+                p.normal_(0.0, 0.03)
             elif "LayerNorm.weight" in n:
                 p.fill_(1.0).add_(0.1 * torch.randn_like(p))
             else:
-                p.normal_(0.0, 0.05)
+                p.normal_(0.0, 0.02)
     model.save_pretrained(CKPT, safe_serialization=True)
     return len(vocab)
 

@@ -68,7 +68,7 @@ def test_reference_arm_reproduces_the_committed_trace():
     assert set(out["trace"]) == set(gold["trace"])
     # run-to-run the reference moves by ~3e-5 in normalised score (fp32 padding-batch effects: a text's batch
     # companions depend on thread completion order), nothing more
-    summary = H.compare_traces(gold, out, score_tol=5e-4)
+    summary = H.compare_traces(gold, out, raw_tol=0.0, floor_tol=5e-4)
     assert not summary["problems"], summary["problems"]
     assert summary["queries"] == len(gold["trace"]) == 12
     # the char-iteration bug (ComoRAG.py:470, 909-935): each tri_retrieve encodes len(query) single characters twice
@@ -106,7 +106,8 @@ def _report(name, payload):
 def test_unmodified_comorag_search_half_on_the_device_matches_the_reference_rankings():
     """install(encoder=False): the reference's own fp32 encoder feeds OUR stores, and unmodified ComoRAG.py runs its
     fact / passage / summary / timeline searches and the synonymy kNN on the device kernels.  Only the bf16 storage
-    of rows and queries separates the two arms, so every ranking must agree to 5e-3 in normalised score."""
+    of rows and queries separates the two arms: raw inner products may move by <= 4e-3, i.e. normalised scores by
+    that over the result's raw range, and rankings must be consistent within the measured deviation."""
     ref = reference_arm()
     calls, restore = _count_device_calls()
     try:
@@ -116,7 +117,7 @@ def test_unmodified_comorag_search_half_on_the_device_matches_the_reference_rank
         restore()
         import comorag_b200.install as crag
         crag.uninstall_search("src.comorag")
-    summary = H.compare_traces(ref, got, score_tol=5e-3)
+    summary = H.compare_traces(ref, got, raw_tol=4e-3)
     _report("e2e_search_half.json", {"summary": summary, "device_calls": calls})
     assert not summary["problems"], summary["problems"]
     n = len(ref["trace"])
@@ -138,10 +139,10 @@ def test_unmodified_comorag_runs_on_the_shim_and_retrieves_what_the_reference_re
     main = sys.modules["src.comorag.ComoRAG"]
     assert main.ComoRAG.get_fact_scores.__module__ == "comorag_b200.comorag_methods"
     assert main.EmbeddingStore.__module__ == "comorag_b200.embedding_store"
-    # the GPU encoder is bf16 against the reference's fp32 HF model, and this 2-layer synthetic checkpoint is badly
-    # conditioned (weights N(0, 0.08)): embedding max-abs error up to 1e-2 moves min-max-normalised scores by up to
-    # a few 1e-2 .. 1e-1.  Rankings must still be consistent within twice the measured deviation of each query.
-    summary = H.compare_traces(ref, got, score_tol=0.25)
+    # the GPU encoder is bf16 against the reference's fp32 HF model (parity bar: embedding max-abs error <= 1e-2, i.e.
+    # raw inner products of unit vectors within ~3e-2); this synthetic 2-layer checkpoint packs all texts into a
+    # narrow cone, so the raw ranges that normalise the scores are small and the normalised deviations large.
+    summary = H.compare_traces(ref, got, raw_tol=3e-2)
     n = len(ref["trace"])
     _report("e2e_full_shim.json", {"summary": summary, "device_calls": calls, "query_encodes": got["query_encodes"],
                                    "reference_query_encodes": ref["query_encodes"]})
@@ -155,5 +156,5 @@ def test_unmodified_comorag_runs_on_the_shim_and_retrieves_what_the_reference_re
     assert ref["query_encodes"]["encoded_texts"] > 5 * got["query_encodes"]["encoded_texts"]
     # the golden trace committed from the build container agrees with the shim as well
     gold = json.load(open(GOLDEN))
-    assert not H.compare_traces(gold, got, score_tol=0.25)["problems"]
+    assert not H.compare_traces(gold, got, raw_tol=3e-2)["problems"]
     torch.cuda.synchronize()
