@@ -70,6 +70,8 @@ class Batcher:
                     break
                 group.append(nxt)
                 total += self._weight(nxt[1])
+            self.batches += 1            # counted before the waiters are released, so stats read after a result are complete
+            self.items += len(group)
             try:
                 results = self._fn(key, [g[1] for g in group])
                 if len(results) != len(group):
@@ -80,8 +82,6 @@ class Batcher:
                 for _, _, fut in group:
                     if not fut.done():
                         fut.set_exception(e)
-            self.batches += 1
-            self.items += len(group)
 
 
 class CoalescedSearch:

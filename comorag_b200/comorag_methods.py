@@ -94,7 +94,97 @@ def prepare_retrieval_objects(self) -> None:
             store.index                # upload / extend the bf16 shard now, as the reference loads its matrices here
         setattr(self, attr, view)
         logger.info(f"prepare_retrieval_objects: self.{attr}.shape = {view.shape}, dtype = {view.dtype}")
+    old = getattr(self, "_crag_wave", None)
+    if old is not None:          # shards were rebuilt: parked results belong to the previous ones
+        old.close()
+        self._crag_wave = None
     self.ready_to_retrieve = True
+
+
+class RetrievalWave:
+    """one batched encode and ONE pass over each of the fact / passage / summary /
+    timeline shards per wave of concurrent `tri_retrieve` calls (ComoRAG.py:436-441 answers questions from up to 16
+    threads, each issuing batch-1 encodes and single-query searches, ComoRAG.py:456-554).
+
+    `get_query_embeddings(query)` -- the first retrieval call of every tri_retrieve (ComoRAG.py:470) -- hands the
+    query to a Batcher; whatever arrived within `max_wait_s` is encoded as one packed forward and scored as one query
+    block per shard (a 16-query pass reads the shard once, like a 1-query pass).  The per-query results are parked and
+    the four scoring entry points of that tri_retrieve (get_fact_scores, dense_passage_retrieval x2,
+    get_similar_summaries) pick them up instead of launching anything."""
+
+    def __init__(self, rag, max_queries: int = 32, max_wait_s: float = 2e-4, keep: int = 256):
+        from collections import OrderedDict
+        import threading
+        from .coalescer import Batcher
+        self.rag = rag
+        self._b = Batcher(self._run, max_items=max_queries, max_wait_s=max_wait_s, name="crag-retrieval-wave")
+        self._results: "OrderedDict[str, dict]" = OrderedDict()
+        self._lock = threading.Lock()
+        self._keep = keep
+
+    @property
+    def stats(self):
+        return {"waves": self._b.batches, "queries": self._b.items}
+
+    def close(self):
+        self._b.close()
+
+    def submit(self, query: str) -> dict:
+        with self._lock:
+            hit = self._results.get(query)
+        if hit is not None:
+            return hit
+        res = self._b.call("tri_retrieve", query)
+        with self._lock:
+            self._results[query] = res
+            while len(self._results) > self._keep:
+                self._results.popitem(last=False)
+        return res
+
+    def lookup(self, query: str):
+        with self._lock:
+            return self._results.get(query)
+
+    def _run(self, key, queries: List[str]) -> List[dict]:
+        rag = self.rag
+        uniq = list(dict.fromkeys(queries))
+        emb = rag.embedding_model.batch_encode(uniq, instruction=_INSTRUCTION_FACT, norm=True)    # one packed forward
+        n = len(uniq)
+        out = [{"embedding": emb[i:i + 1]} for i in range(n)]
+        fact_index = rag.fact_embeddings.index
+        q_dev = fact_index.prepare_queries(emb)                  # one H2D of the wave's query block
+        scores, mm = fact_index.scores_device(q_dev)             # one pass over the fact shard for the whole wave
+        facts = retrieval.normalize_topk_scores(scores.cpu().numpy(), mm.cpu().numpy())
+        for i in range(n):
+            out[i]["fact_scores"] = facts[i]
+        shards = [("passages", rag.passage_embeddings.index)]
+        if rag.global_config.need_cluster:
+            shards.append(("summaries", rag.summary_embeddings.index))
+        for name, index in shards:
+            scores, mm = index.scores_device(q_dev)              # one pass per shard
+            mm_h = mm.cpu().numpy()
+            for i in range(n):
+                order, sorted_scores = index.rank_device(scores[i].contiguous())
+                out[i][name] = (order.cpu().numpy(),
+                                retrieval.normalize_topk_scores(sorted_scores.cpu().numpy()[None, :], mm_h[i:i + 1])[0])
+        level_store = getattr(rag, "level_store", None)
+        if level_store is not None and hasattr(level_store, "search") and len(level_store.hash_ids):
+            k = min(int(getattr(rag.global_config, "qa_epi_top_k", 50)), len(level_store.hash_ids))
+            ids, sc, mm = level_store.search(emb, k)             # one fused top-k pass over the timeline shard
+            norm = retrieval.normalize_topk_scores(sc, mm)
+            for i in range(n):
+                out[i]["timeline"] = (id(level_store), k,
+                                      [level_store.texts[j] for j in ids[i] if j >= 0],
+                                      [float(s) for s, j in zip(norm[i], ids[i]) if j >= 0])
+        by_query = dict(zip(uniq, out))
+        return [by_query[q] for q in queries]
+
+
+def _wave(self):
+    w = getattr(self, "_crag_wave", None)
+    if w is None and getattr(self.global_config, "retrieval_wave", True) and isinstance(getattr(self, "fact_embeddings", None), ShardMatrix):
+        w = self._crag_wave = RetrievalWave(self)
+    return w
 
 
 def get_query_embeddings(self, queries) -> None:
@@ -103,6 +193,14 @@ def get_query_embeddings(self, queries) -> None:
     is one query: it is encoded once per cache and the later lookups (get_fact_scores, dense_passage_retrieval, both
     need_cluster settings) hit.  Lists of str / QuerySolution behave as in the reference."""
     if isinstance(queries, str):
+        wave = _wave(self)
+        if wave is not None and len(self.fact_node_keys) and len(self.passage_node_keys):
+            res = wave.submit(queries)       # encode + all four shard passes, shared with concurrent callers
+            self.query_to_embedding['triple'][queries] = res["embedding"]
+            self.query_to_embedding['passage'][queries] = res["embedding"]
+            if "timeline" in res:
+                retrieval.park_similar_summaries(queries, res["timeline"])
+            return
         queries = [queries]
     cache = self.query_to_embedding
     todo: List[str] = []
@@ -135,6 +233,10 @@ def _query_embedding(self, which: str, query: str, instruction: str) -> np.ndarr
 
 def get_fact_scores(self, query: str) -> np.ndarray:
     """ComoRAG.py:937-948: min-max-normalised score of every fact, fp32 [N_f] in fact_node_keys order."""
+    wave = getattr(self, "_crag_wave", None)
+    hit = wave.lookup(query) if wave is not None else None
+    if hit is not None:
+        return hit["fact_scores"]
     query_embedding = _query_embedding(self, 'triple', query, _INSTRUCTION_FACT)
     return retrieval.get_fact_scores(self.fact_embeddings.index, query_embedding)
 
@@ -143,6 +245,12 @@ def dense_passage_retrieval(self, query: str, need_cluster: bool = False) -> Tup
     """ComoRAG.py:950-967: (sorted_doc_ids int64 [N], sorted min-max scores fp32 [N]) over the passage shard
     (need_cluster=False) or the summary shard (True) -- the FULL permutation, as graph_search_with_fact_entities
     consumes every rank (ComoRAG.py:1034-1042)."""
+    wave = getattr(self, "_crag_wave", None)
+    hit = wave.lookup(query) if wave is not None else None
+    name = "summaries" if need_cluster else "passages"
+    if hit is not None and name in hit:
+        order, scores = hit[name]
+        return order.copy(), scores.copy()
     query_embedding = _query_embedding(self, 'passage', query, _INSTRUCTION_PASSAGE)
     docs = self.summary_embeddings if need_cluster else self.passage_embeddings
     return retrieval.dense_passage_retrieval(docs.index, query_embedding)

@@ -73,12 +73,30 @@ def get_fact_scores_topk(index: DenseIndex, query_embedding, link_top_k: int) ->
     return ids[0], sc[0]
 
 
+_parked_summaries: "dict" = {}
+_parked_lock = __import__("threading").Lock()
+
+
+def park_similar_summaries(query: str, result) -> None:
+    """A retrieval wave (comorag_methods.RetrievalWave) already ran the timeline search for `query`; keep its
+    (store id, k, texts, scores) until get_similar_summaries asks for it."""
+    with _parked_lock:
+        _parked_summaries[query] = result
+        while len(_parked_summaries) > 512:
+            _parked_summaries.pop(next(iter(_parked_summaries)))
+
+
 def get_similar_summaries(query: str, level_store, embedding_model, top_k: int = 3,
                           instruction: Optional[str] = None) -> Tuple[List[str], List[float]]:
     """embed_utils.py:109-161 on an engine EmbeddingStore: no per-call matrix rebuild, fused top-k."""
     level_ids = level_store.get_all_ids()
     if not level_ids:
         return [], []
+    with _parked_lock:
+        parked = _parked_summaries.get(query)
+    if parked is not None and parked[0] == id(level_store) and parked[1] >= min(top_k, len(level_ids)):
+        k = min(top_k, len(level_ids))
+        return list(parked[2][:k]), list(parked[3][:k])
     query_embedding = embedding_model.batch_encode(
         query, instruction='Given a question, retrieve relevant documents that best answer the question.', norm=True)
     k = min(top_k, len(level_ids))

@@ -433,11 +433,15 @@ def run_cinderella(arm: str, workdir: str, ref_root: str, max_loops: int = 1, qu
                 "timeline": rag.level_store.get_all_ids(),
             }
             n_edges = rag.graph.ecount()
+            wave = getattr(rag, "_crag_wave", None)
+            wave_stats = dict(wave.stats) if wave is not None else None
+            if wave is not None:
+                wave.close()
     finally:
         for name, original in wrapped.items():
             setattr(cls, name, original)
         main.get_similar_summaries = orig_gss
-    return {"arm": arm, "trace": trace, "answers": [getattr(s, "answer", None) for s in solutions], "stores": stores,
+    return {"arm": arm, "wave_stats": wave_stats if arm != "reference" else None, "trace": trace, "answers": [getattr(s, "answer", None) for s in solutions], "stores": stores,
             "graph_edges": n_edges, "index_encodes": index_encodes,
             "query_encodes": {k: counters[k] - index_encodes[k] for k in counters}, "queries": queries}
 

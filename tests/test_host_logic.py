@@ -275,3 +275,98 @@ def test_token_flattening_matches_the_plain_loops():
         _flatten([[1, 2], []])
     with pytest.raises(ValueError):
         _flatten([])
+
+
+def test_retrieval_wave_shares_one_pass_per_shard_between_concurrent_tri_retrieves():
+    """SURVEY 8f item 1 (host logic, CPU stand-ins for the device entry points): 12 threads run the retrieval calls of
+    tri_retrieve (ComoRAG.py:470-531) for 24 queries; every caller gets exactly what an un-coalesced call returns,
+    while encodes and shard passes are shared."""
+    import threading
+    import time
+    import types
+    from concurrent.futures import ThreadPoolExecutor
+
+    import torch
+    from comorag_b200 import comorag_methods as cm
+    from comorag_b200 import retrieval as rt
+
+    rng = np.random.default_rng(3)
+    D = 16
+    mats = {name: rng.standard_normal((n, D)).astype(np.float32) for name, n in (("fact", 40), ("chunk", 9), ("summary", 5), ("level", 4))}
+    passes = {name: 0 for name in mats}
+    encodes = []
+
+    class FakeIndex:
+        def __init__(self, name):
+            self.name, self.E = name, torch.from_numpy(mats[name])
+
+        def prepare_queries(self, q):
+            return torch.as_tensor(np.asarray(q, np.float32))
+
+        def scores_device(self, q):
+            passes[self.name] += 1
+            time.sleep(0.002)
+            sc = q @ self.E.T
+            return sc, torch.stack([sc.min(1).values, sc.max(1).values], 1)
+
+        def rank_device(self, row):
+            order = torch.argsort(row, descending=True, stable=True)
+            return order, row[order]
+
+    class FakeStore:
+        def __init__(self, name):
+            self.index = FakeIndex(name)
+            self.hash_ids = [f"{name}-{i}" for i in range(mats[name].shape[0])]
+            self.texts = [f"{name} text {i}" for i in range(mats[name].shape[0])]
+            self._dim = D
+
+        def get_all_ids(self):
+            return list(self.hash_ids)
+
+        def search(self, q, k):
+            passes[self.index.name] += 1
+            sc = np.asarray(q, np.float32) @ mats[self.index.name].T
+            ids = np.argsort(-sc, axis=1, kind="stable")[:, :k]
+            return ids, np.take_along_axis(sc, ids, 1), np.stack([sc.min(1), sc.max(1)], 1)
+
+    class FakeModel:
+        def batch_encode(self, texts, **kw):
+            texts = [texts] if isinstance(texts, str) else list(texts)
+            encodes.append(len(texts))
+            time.sleep(0.001)
+            return np.stack([np.random.default_rng(abs(hash(t)) % (2 ** 32)).standard_normal(D).astype(np.float32) for t in texts])
+
+    stores = {n: FakeStore(n) for n in mats}
+    rag = types.SimpleNamespace(
+        global_config=types.SimpleNamespace(need_cluster=True, qa_epi_top_k=3), embedding_model=FakeModel(),
+        fact_embeddings=cm.ShardMatrix(stores["fact"]), passage_embeddings=cm.ShardMatrix(stores["chunk"]),
+        summary_embeddings=cm.ShardMatrix(stores["summary"]), level_store=stores["level"],
+        fact_node_keys=stores["fact"].hash_ids, passage_node_keys=stores["chunk"].hash_ids,
+        query_to_embedding={"triple": {}, "passage": {}})
+    queries = [f"probe number {i}" for i in range(24)]
+
+    def tri_retrieve(q):
+        cm.get_query_embeddings(rag, q)
+        facts = cm.get_fact_scores(rag, q)
+        ver = cm.dense_passage_retrieval(rag, q)
+        sem = cm.dense_passage_retrieval(rag, q, need_cluster=True)
+        epi = rt.get_similar_summaries(q, rag.level_store, rag.embedding_model, top_k=3)
+        return facts, ver, sem, epi
+
+    with ThreadPoolExecutor(12) as ex:
+        got = list(ex.map(tri_retrieve, queries))
+    stats = rag._crag_wave.stats
+    rag._crag_wave.close()
+    assert stats["queries"] == 24 and stats["waves"] < 24
+    assert sum(encodes) == 24 and len(encodes) == stats["waves"]             # one packed encode per wave, nothing else
+    assert passes["fact"] == passes["chunk"] == passes["summary"] == passes["level"] == stats["waves"]
+    for q, (facts, ver, sem, epi) in zip(queries, got):
+        e = FakeModel().batch_encode(q)
+        np.testing.assert_allclose(facts, so.fact_scores(mats["fact"], e), atol=1e-6)
+        for (ids, sc), name in ((ver, "chunk"), (sem, "summary")):
+            w_ids, w_sc = so.dense_passage_retrieval(mats[name], e)
+            np.testing.assert_array_equal(ids, w_ids)
+            np.testing.assert_allclose(sc, w_sc, atol=1e-6)
+        raw = (e @ mats["level"].T)[0]
+        want = np.argsort(-raw, kind="stable")[:3]
+        assert epi[0] == [f"level text {i}" for i in want]

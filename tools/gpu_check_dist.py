@@ -24,7 +24,10 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     results = []
-    for n, dim, nq, k in [(100_003, 1024, 32, 10), (5, 64, 3, 10), (40_000, 768, 40, 100), (1_000_000, 1024, 32, 10)]:
+    shapes = [(100_003, 1024, 32, 10), (5, 64, 3, 10), (40_000, 768, 40, 100), (1_000_000, 1024, 32, 10)]
+    if os.environ.get("CHECK_HEADLINE", "1") != "0":     # BASELINE config 3 at its named shape, k = 10 and 100
+        shapes += [(10_000_000, 1024, 32, 10), (10_000_000, 1024, 32, 100)]
+    for n, dim, nq, k in shapes:
         corpus = make_unit_rows(n, dim, 77, device=dev)          # identical on every rank (same seed, same device type)
         queries = make_unit_rows(nq, dim, 78, device=dev)
         offs = shard_bounds(n, world)
@@ -35,7 +38,12 @@ def main():
         ok = bool(torch.equal(ids, w_ids) and torch.equal(scores, w_scores) and torch.equal(mm, w_mm))
         flag = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        results.append({"shape": [n, dim, nq, k], "world": world, "all_ranks_equal_single_gpu": bool(flag.item())})
+        results.append({"shape": [n, dim, nq, k], "world": world, "exchange": idx.exchange_mode,
+                        "all_ranks_equal_single_gpu": bool(flag.item())})
+        if idx.peer is not None:
+            idx.peer.check()
+        del corpus, shard, idx
+        torch.cuda.empty_cache()
     # row-sharded IVF (shared centroids, per-rank residual lists) == the single-GPU IVF over the whole corpus
     from comorag_b200.ivf import IVFIndex, ShardedIVF, spherical_kmeans
     for n, dim, nlist, nprobe, nq, k in [(60_000, 768, 64, 8, 32, 100), (9_000, 128, 32, 32, 5, 10)]:
