@@ -576,6 +576,14 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const floa
   if ((uintptr_t(a) | uintptr_t(w) | uintptr_t(out) | uintptr_t(bias) | uintptr_t(residual)) & 15) return fail(CRAG_ERR_INVALID, "gemm: pointers must be 16-byte aligned");
   bool wide = (N % 256 == 0) || N >= 1024;
   if (variant & 2) wide = false;  // A/B switch: force the BN = 128 tile
+  // Short batches (the query side: a wave of <= 32 probes is a few hundred tokens): a 256 x 256 pair tile leaves
+  // most SMs idle and serialises the whole K loop on a handful of CTAs (FFN-down at M = 768: 12 pair tiles x 64
+  // k-blocks).  128 x 128 single-CTA tiles give 4x the CTAs and a K loop per CTA that is half as long.
+  static const int small_m = [] { const char* e = getenv("CRAG_GEMM_SMALL_M"); return e ? atoi(e) : 1024; }();
+  if (M <= small_m && !(variant & 8)) {
+    variant |= 1;
+    wide = false;
+  }
   const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(residual);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   CUtensorMap tm_a, tm_b;

@@ -37,87 +37,65 @@ constexpr int kAccStages = 16;       // score-tile buffers in TMEM: the scan may
 constexpr uint32_t kTmemCols = kAccStages * kNQ;  // 512 columns = all of TMEM (1 CTA per SM)
 
 // Pooled admission floor.  Every CTA publishes its current best kPoolM KEYS per query (after each flush of that
-// query's candidate buffer) in pool[q][cta][kPoolM] (packed u64 keys, 0 = nothing yet).  Published keys belong to
-// distinct rows of THIS shard (one CTA's j-th best key only ever improves, so values read at different times still
-// stand for distinct rows at least that good), hence the k-th largest pooled key is a key that at least k shard rows
-// reach: no row with a smaller key can rank in the top-k.  Each CTA recomputes that k-th key from time to time
-// (after tiles 2, 12, 48 and every 128th) and raises its admission thresholds to it, so all CTAs work with
-// (almost) the global k-th best seen so far instead of their private one.  This replaces the separate sample
-// pre-pass of round 1 (two launches fewer), cuts admissions at k = 100 by about two orders of magnitude, and --
-// because the floor is a full key, row id included -- keeps tie-heavy corpora (duplicate rows) from flooding the
-// selector with rows that only tie the k-th score.
+// query's candidate buffer) in pool[cta][m][q] (packed u64 keys, 0 = nothing yet; query-contiguous so a warp reads
+// one CTA's entry for all 32 queries as a single 256-byte line).  Published keys belong to distinct rows of THIS
+// shard (one CTA's j-th best key only ever improves, so values read at different times still stand for distinct rows
+// at least that good).  A refresh (after tiles 2, 12, 48 and every 128th) turns them into a floor key per query:
+// select warp w looks at the CTAs c = w (mod 4), each LANE keeps the kp = ceil(k / 4) largest keys of ITS query in
+// registers (no cross-lane traffic at all), and the floor is the minimum over the four warps of their kp-th largest:
+// every quarter of the CTAs then holds kp rows at or above it, i.e. at least k shard rows reach the floor and no row
+// with a smaller key can rank in the top-k.  All CTAs thus work with (almost) the global k-th best seen so far
+// instead of their private one.  This replaces the separate sample pre-pass of round 1 (two launches fewer), cuts
+// admissions at k = 100 by about two orders of magnitude, and -- because the floor is a full key, row id included --
+// keeps tie-heavy corpora (duplicate rows) from flooding the selector with rows that only tie the k-th score.
 constexpr int kPoolM = 4;
-constexpr int kPoolMaxCtas = 160;   // 5 entries per lane
-constexpr int kPoolSmallK = 16;     // up to this k only each CTA's BEST key is pooled (148 values decide a top-16 floor)
+constexpr int kPoolMaxCtas = 160;
+constexpr int kPoolSmallK = 16;     // up to this k only each CTA's BEST key is pooled (37 CTA maxima per warp decide)
 
-// k-th largest of the NV keys each lane holds (hi = score word, lo = row word), 0 when fewer than k are set.
-// Bisection on the score bits, counted with four independent accumulators (the select warps run one warp per
-// scheduler, so a serial chain of NV dependent adds would cost its full latency 32 times); ties at the k-th score
-// (duplicate rows) are resolved by a second bisection on the row word, otherwise a single min-reduce finishes.
-template <int NV>
-__device__ __forceinline__ uint64_t kth_largest_key(const uint32_t (&hi)[NV], const uint32_t (&lo)[NV], int k) {
-  auto count_ge = [&](uint32_t cand) -> int {
-    int c[4] = {0, 0, 0, 0};
+// kp-th largest (kp <= KP) of the keys query `q` (= lane) finds in the pool entries of CTAs w, w + 4, ...
+template <int KP>
+__device__ __forceinline__ uint64_t lane_kth_of_pool(const uint64_t* __restrict__ pool, int n_ctas, int w, int q,
+                                                     int m_eff, int kp) {
+  uint64_t t[KP];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) c[i & 3] += (hi[i] >= cand) ? 1 : 0;
-    return __reduce_add_sync(0xffffffffu, (c[0] + c[1]) + (c[2] + c[3]));
+  for (int j = 0; j < KP; ++j) t[j] = 0ull;
+  auto offer = [&](uint64_t v) {
+    if (v <= t[KP - 1]) return;
+#pragma unroll
+    for (int j = KP - 1; j >= 1; --j) {
+      if (v > t[j - 1]) t[j] = t[j - 1];
+      else if (v > t[j]) t[j] = v;
+    }
+    if (v > t[0]) t[0] = v;
   };
-  uint32_t t = 0;
-#pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t cand = t | (1u << bit);
-    if (count_ge(cand) >= k) t = cand;
-  }
-  if (t == 0) return 0ull;   // fewer than k rows published so far
-  int c_gt = 0, c_eq = 0;
-  uint32_t lo_min = 0xFFFFFFFFu;
+  constexpr int U = 8;   // loads in flight per lane (L2 latency ~1 us: the entries of 8 CTAs travel together)
+  if (m_eff == 1) {
+    for (int c0 = w; c0 < n_ctas; c0 += 4 * U) {
+      uint64_t v[U];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    c_gt += (hi[i] > t) ? 1 : 0;
-    if (hi[i] == t) { ++c_eq; lo_min = lo[i] < lo_min ? lo[i] : lo_min; }
-  }
-  c_gt = __reduce_add_sync(0xffffffffu, c_gt);
-  c_eq = __reduce_add_sync(0xffffffffu, c_eq);
-  const int need = k - c_gt;             // rank wanted among the keys that share the k-th score (>= 1, <= c_eq)
-  if (need >= c_eq) return (uint64_t(t) << 32) | __reduce_min_sync(0xffffffffu, lo_min);   // the usual case: no tie
-  uint32_t l = 0;
-#pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t cand = l | (1u << bit);
-    int c = 0;
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + 4 * u;
+        v[u] = c < n_ctas ? __ldcg(pool + (size_t(c) * kPoolM) * kNQ + q) : 0ull;
+      }
 #pragma unroll
-    for (int i = 0; i < NV; ++i) c += (hi[i] == t && lo[i] >= cand) ? 1 : 0;
-    if (__reduce_add_sync(0xffffffffu, c) >= need) l = cand;
-  }
-  return (uint64_t(t) << 32) | l;
-}
-
-__device__ __forceinline__ uint64_t pooled_floor_key(const uint64_t* __restrict__ pool_q, int n_ctas, int k, int lane) {
-  if (k <= kPoolSmallK) {
-    uint32_t hi[kPoolMaxCtas / 32], lo[kPoolMaxCtas / 32];
-#pragma unroll
-    for (int i = 0; i < kPoolMaxCtas / 32; ++i) {
-      const int c = lane + 32 * i;
-      const uint64_t x = c < n_ctas ? __ldcg(pool_q + size_t(c) * kPoolM) : 0ull;   // L2: other SMs keep updating it
-      lo[i] = uint32_t(x);
-      hi[i] = uint32_t(x >> 32);
+      for (int u = 0; u < U; ++u) offer(v[u]);
     }
-    return kth_largest_key<kPoolMaxCtas / 32>(hi, lo, k);
-  }
-  constexpr int NV = (kPoolMaxCtas / 32) * kPoolM;
-  uint32_t hi[NV], lo[NV];
+  } else {
+    for (int c0 = w; c0 < n_ctas; c0 += 4 * (U / 4)) {
+      uint64_t v[U];
 #pragma unroll
-  for (int i = 0; i < kPoolMaxCtas / 32; ++i) {
-    const int c = lane + 32 * i;
-    uint4 x = make_uint4(0u, 0u, 0u, 0u), y = make_uint4(0u, 0u, 0u, 0u);
-    if (c < n_ctas) {
-      x = __ldcg(reinterpret_cast<const uint4*>(pool_q) + 2 * c);
-      y = __ldcg(reinterpret_cast<const uint4*>(pool_q) + 2 * c + 1);
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + 4 * (u / kPoolM);
+        v[u] = c < n_ctas ? __ldcg(pool + (size_t(c) * kPoolM + (u % kPoolM)) * kNQ + q) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) offer(v[u]);
     }
-    lo[4 * i + 0] = x.x; hi[4 * i + 0] = x.y; lo[4 * i + 1] = x.z; hi[4 * i + 1] = x.w;
-    lo[4 * i + 2] = y.x; hi[4 * i + 2] = y.y; lo[4 * i + 3] = y.z; hi[4 * i + 3] = y.w;
   }
-  return kth_largest_key<NV>(hi, lo, k);
+  uint64_t r = 0ull;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) r = (j == kp - 1) ? t[j] : r;
+  return r;
 }
 
 template <int KLIST, int CAP, int STAGES>
@@ -131,6 +109,7 @@ struct SearchLayout {
            + kNQ * 4               // cnt
            + kNQ * 8 + kNQ * 4     // continuation bound (key, score)
            + kNQ * 8               // pooled admission floor (key)
+           + 4 * kNQ * 8           // per-warp partial floors of a refresh
            + 4 * kNQ * 2 * 4       // min/max cross-warp reduction
            + 16;                   // tmem base
   }
@@ -188,8 +167,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
   float* red = reinterpret_cast<float*>(cnt + kNQ);        // [4][kNQ][2]
   uint64_t* bnd_key = reinterpret_cast<uint64_t*>(red + 4 * kNQ * 2);  // [kNQ] admit only keys < bnd_key
   float* bnd_f = reinterpret_cast<float*>(bnd_key + kNQ);              // [kNQ] score part of the bound
-  uint64_t* floor_key = reinterpret_cast<uint64_t*>(bnd_f + kNQ);      // [kNQ] pooled admission floor (see pooled_floor_key)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(floor_key + kNQ);
+  uint64_t* floor_key = reinterpret_cast<uint64_t*>(bnd_f + kNQ);      // [kNQ] pooled admission floor (see kPoolM)
+  uint64_t* part_floor = floor_key + kNQ;                              // [4][kNQ] scratch of a floor refresh
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_floor + 4 * kNQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -314,15 +294,29 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
     auto publish = [&](int q) {
       if (pool != nullptr && lane < kPoolM) {
         const uint64_t kk = keys[q * L::kKeysPerQuery + lane];
-        if (kk) pool[(size_t(q) * gridDim.x + blockIdx.x) * kPoolM + lane] = kk;
+        if (kk) pool[(size_t(blockIdx.x) * kPoolM + lane) * kNQ + q] = kk;
       }
     };
-    // raise the owned queries' thresholds to the pooled floor
+    // raise the thresholds to the pooled floor (all four select warps; see the comment at kPoolM)
     auto refresh = [&]() {
       if (pool == nullptr) return;
-      for (int q = ew; q < nq; q += 4) {
-        const uint64_t pf = pooled_floor_key(pool + size_t(q) * gridDim.x * kPoolM, int(gridDim.x), k, lane);
-        if (lane == 0 && pf > floor_key[q]) {
+      const int m_eff = k <= kPoolSmallK ? 1 : kPoolM;
+      const int kp = (k + 3) / 4;
+      uint64_t f;
+      if (KLIST <= 64) {
+        f = (kp <= 4) ? lane_kth_of_pool<4>(pool, int(gridDim.x), ew, lane, m_eff, kp)
+                      : lane_kth_of_pool<16>(pool, int(gridDim.x), ew, lane, m_eff, kp);
+      } else {
+        f = lane_kth_of_pool<32>(pool, int(gridDim.x), ew, lane, m_eff, kp);
+      }
+      part_floor[ew * kNQ + lane] = f;
+      named_bar_sync(1, kEpiThreads);
+      if (lane < kNQ / 4) {                      // this warp owns queries ew, ew + 4, ...
+        const int q = ew + 4 * lane;
+        uint64_t pf = part_floor[q];
+#pragma unroll
+        for (int w2 = 1; w2 < 4; ++w2) pf = part_floor[w2 * kNQ + q] < pf ? part_floor[w2 * kNQ + q] : pf;
+        if (q < nq && pf > floor_key[q]) {
           floor_key[q] = pf;
           if (pf > thr_key[q]) {
             thr_key[q] = pf;
@@ -420,7 +414,8 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
               ((pending >> q) & 1u) ? make_key(__uint_as_float(r[q]), uint32_t(row)) : 0ull;
         named_bar_sync(1, kEpiThreads);
         for (int q = ew; q < kNQ; q += 4) {
-          flush_query<KLIST, CAP>(keys + q * L::kKeysPerQuery, 128 - KLIST, k, &thr_key[q], lane);
+          // exactly 128 keys are live (slots 0..127): sort those, not the whole KLIST + CAP area
+          flush_query<KLIST, 128 - KLIST>(keys + q * L::kKeysPerQuery, 128 - KLIST, k, &thr_key[q], lane);
           if (lane == 0) settle(q);
           publish(q);
         }

@@ -136,6 +136,35 @@ def test_forward_vs_torch_oracle(dev, cargs, lens, std):
     assert float((alone[0] - out[0]).abs().max()) < 1e-6
 
 
+def test_bge_large_256_mixed_length_chunks_centred_cosine(dev):
+    """SURVEY.md 8d at its stated size: >= 256 chunks, lengths U[32, 512], the bge-large shape (24 layers).  With HF's
+    default init every embedding collapses onto one direction and a plain cosine is vacuous, so the word embeddings
+    get unit scale (texts then differ) and the cosine is ALSO taken after removing the mean embedding of the batch:
+    that centred cosine only stays high if the per-text part of the embedding is right."""
+    from comorag_b200.encoder import BertEncoderB200, EncoderConfig, random_state_dict
+    cfg = EncoderConfig(1024, 24, 16, 4096, 30522)
+    sd = random_state_dict(cfg, seed=3, std=0.02, device=dev)
+    sd["embeddings.word_embeddings.weight"] = sd["embeddings.word_embeddings.weight"] * 50.0     # std 1.0
+    enc = BertEncoderB200(cfg, sd, dev)
+    g = torch.Generator().manual_seed(11)
+    lens = torch.randint(32, 513, (256,), generator=g).tolist()
+    seqs = [[101] + torch.randint(1000, cfg.vocab_size, (L - 2,), generator=g).tolist() + [102] for L in lens]
+    outs = []
+    for s0 in range(0, 256, 64):                      # 64 chunks (~17k tokens) per packed forward
+        outs.append(enc.encode_token_lists(seqs[s0:s0 + 64]))
+    out = torch.cat(outs, 0)
+    sd_q = {k: (v.bfloat16().float() if v.dim() == 2 else v) for k, v in sd.items()}
+    ref = eo.encode_token_lists(sd_q, cfg, seqs)
+    cos = torch.nn.functional.cosine_similarity(out, ref, dim=1)
+    mean = ref.mean(dim=0, keepdim=True)
+    ccos = torch.nn.functional.cosine_similarity(out - mean, ref - mean, dim=1)
+    spread = float(torch.nn.functional.cosine_similarity(ref[:128], ref[128:], dim=1).mean())
+    err = float((out - ref).abs().max())
+    assert spread < 0.9, f"the synthetic embeddings collapsed (mean pair cosine {spread:.4f}): the test would be vacuous"
+    assert float(cos.min()) > 0.999 and err < 1e-2, (float(cos.min()), err)
+    assert float(ccos.min()) > 0.99, f"centred cosine {float(ccos.min()):.5f} (plain {float(cos.min()):.6f}, max-abs {err:.2e})"
+
+
 def test_dropin_model_matches_reference_embeddings(dev, gold):
     """BGEEmbeddingModel (ours) on the synthetic checkpoint vs what the REFERENCE's BGEEmbeddingModel returned."""
     from comorag_b200.config import EngineConfig
