@@ -40,11 +40,12 @@ constexpr uint32_t kTmemCols = kAccStages * kNQ;  // 512 columns = all of TMEM (
 // query's candidate buffer) in pool[cta][m][q] (packed u64 keys, 0 = nothing yet; query-contiguous so a warp reads
 // one CTA's entry for all 32 queries as a single 256-byte line).  Published keys belong to distinct rows of THIS
 // shard (one CTA's j-th best key only ever improves, so values read at different times still stand for distinct rows
-// at least that good).  A refresh (after tiles 2, 12, 48 and every 128th) turns them into a floor key per query:
-// select warp w looks at the CTAs c = w (mod 4), each LANE keeps the kp = ceil(k / 4) largest keys of ITS query in
-// registers (no cross-lane traffic at all), and the floor is the minimum over the four warps of their kp-th largest:
-// every quarter of the CTAs then holds kp rows at or above it, i.e. at least k shard rows reach the floor and no row
-// with a smaller key can rank in the top-k.  All CTAs thus work with (almost) the global k-th best seen so far
+// at least that good).  A refresh turns them into a floor key per query.  For k <= 16 (after tiles 2, 12, 48 and
+// every 128th): select warp w looks at the BEST key of the CTAs c = w (mod 4), each LANE keeps the kp = ceil(k / 4)
+// largest of ITS query in registers (no cross-lane traffic at all), and the floor is the minimum over the four warps
+// of their kp-th largest: every quarter of the CTAs then holds kp rows at or above it, i.e. at least k shard rows
+// reach the floor and no row with a smaller key can rank in the top-k.  For larger k (after tiles 2, 4, 8, 16, 32
+// and every 64th): the warp owning a query finds the k-th largest of ALL pooled keys by bisection (pooled_kth_key).  All CTAs thus work with (almost) the global k-th best seen so far
 // instead of their private one.  This replaces the separate sample pre-pass of round 1 (two launches fewer), cuts
 // admissions at k = 100 by about two orders of magnitude, and -- because the floor is a full key, row id included --
 // keeps tie-heavy corpora (duplicate rows) from flooding the selector with rows that only tie the k-th score.
@@ -96,6 +97,64 @@ __device__ __forceinline__ uint64_t lane_kth_of_pool(const uint64_t* __restrict_
 #pragma unroll
   for (int j = 0; j < KP; ++j) r = (j == kp - 1) ? t[j] : r;
   return r;
+}
+
+// k > kPoolSmallK: the owning warp of a query pools ALL CTAs' kPoolM keys (20 per lane) and finds their k-th largest
+// by bisection on the score bits (four independent counters per step; ties at the k-th score -- duplicate rows --
+// are resolved by a second bisection on the row word).  Per-lane top-k lists, as used for small k, would need
+// k / 4 registers per lane and an insertion chain that long; measured slower by 35 % at k = 100.
+template <int NV>
+__device__ __forceinline__ uint64_t kth_largest_key(const uint32_t (&hi)[NV], const uint32_t (&lo)[NV], int k) {
+  auto count_ge = [&](uint32_t cand) -> int {
+    int c[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < NV; ++i) c[i & 3] += (hi[i] >= cand) ? 1 : 0;
+    return __reduce_add_sync(0xffffffffu, (c[0] + c[1]) + (c[2] + c[3]));
+  };
+  uint32_t t = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = t | (1u << bit);
+    if (count_ge(cand) >= k) t = cand;
+  }
+  if (t == 0) return 0ull;   // fewer than k rows published so far
+  int c_gt = 0, c_eq = 0;
+  uint32_t lo_min = 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    c_gt += (hi[i] > t) ? 1 : 0;
+    if (hi[i] == t) { ++c_eq; lo_min = lo[i] < lo_min ? lo[i] : lo_min; }
+  }
+  c_gt = __reduce_add_sync(0xffffffffu, c_gt);
+  c_eq = __reduce_add_sync(0xffffffffu, c_eq);
+  const int need = k - c_gt;             // rank wanted among the keys that share the k-th score (>= 1, <= c_eq)
+  if (need >= c_eq) return (uint64_t(t) << 32) | __reduce_min_sync(0xffffffffu, lo_min);   // the usual case: no tie
+  uint32_t l = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = l | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) c += (hi[i] == t && lo[i] >= cand) ? 1 : 0;
+    if (__reduce_add_sync(0xffffffffu, c) >= need) l = cand;
+  }
+  return (uint64_t(t) << 32) | l;
+}
+
+__device__ __forceinline__ uint64_t pooled_kth_key(const uint64_t* __restrict__ pool, int n_ctas, int q, int k, int lane) {
+  constexpr int NV = (kPoolMaxCtas / 32) * kPoolM;
+  uint32_t hi[NV], lo[NV];
+#pragma unroll
+  for (int i = 0; i < kPoolMaxCtas / 32; ++i) {
+    const int c = lane + 32 * i;
+#pragma unroll
+    for (int m = 0; m < kPoolM; ++m) {
+      const uint64_t x = c < n_ctas ? __ldcg(pool + (size_t(c) * kPoolM + m) * kNQ + q) : 0ull;
+      lo[kPoolM * i + m] = uint32_t(x);
+      hi[kPoolM * i + m] = uint32_t(x >> 32);
+    }
+  }
+  return kth_largest_key<NV>(hi, lo, k);
 }
 
 template <int KLIST, int CAP, int STAGES>
@@ -298,30 +357,32 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       }
     };
     // raise the thresholds to the pooled floor (all four select warps; see the comment at kPoolM)
+    auto raise_to = [&](int q, uint64_t pf) {
+      if (q < nq && pf > floor_key[q]) {
+        floor_key[q] = pf;
+        if (pf > thr_key[q]) {
+          thr_key[q] = pf;
+          thr_f[q] = key_score(pf);
+        }
+      }
+    };
     auto refresh = [&]() {
       if (pool == nullptr) return;
-      const int m_eff = k <= kPoolSmallK ? 1 : kPoolM;
-      const int kp = (k + 3) / 4;
-      uint64_t f;
-      if (KLIST <= 64) {
-        f = (kp <= 4) ? lane_kth_of_pool<4>(pool, int(gridDim.x), ew, lane, m_eff, kp)
-                      : lane_kth_of_pool<16>(pool, int(gridDim.x), ew, lane, m_eff, kp);
-      } else {
-        f = lane_kth_of_pool<32>(pool, int(gridDim.x), ew, lane, m_eff, kp);
-      }
-      part_floor[ew * kNQ + lane] = f;
-      named_bar_sync(1, kEpiThreads);
-      if (lane < kNQ / 4) {                      // this warp owns queries ew, ew + 4, ...
-        const int q = ew + 4 * lane;
-        uint64_t pf = part_floor[q];
+      if (k <= kPoolSmallK) {
+        // lane = query: every warp scans a quarter of the CTAs' best keys, the floor is the minimum of the four
+        part_floor[ew * kNQ + lane] = lane_kth_of_pool<4>(pool, int(gridDim.x), ew, lane, 1, (k + 3) / 4);
+        named_bar_sync(1, kEpiThreads);
+        if (lane < kNQ / 4) {                      // this warp owns queries ew, ew + 4, ...
+          const int q = ew + 4 * lane;
+          uint64_t pf = part_floor[q];
 #pragma unroll
-        for (int w2 = 1; w2 < 4; ++w2) pf = part_floor[w2 * kNQ + q] < pf ? part_floor[w2 * kNQ + q] : pf;
-        if (q < nq && pf > floor_key[q]) {
-          floor_key[q] = pf;
-          if (pf > thr_key[q]) {
-            thr_key[q] = pf;
-            thr_f[q] = key_score(pf);
-          }
+          for (int w2 = 1; w2 < 4; ++w2) pf = part_floor[w2 * kNQ + q] < pf ? part_floor[w2 * kNQ + q] : pf;
+          raise_to(q, pf);
+        }
+      } else {
+        for (int q = ew; q < nq; q += 4) {
+          const uint64_t pf = pooled_kth_key(pool, int(gridDim.x), q, k, lane);
+          if (lane == 0) raise_to(q, pf);
         }
       }
     };
@@ -340,7 +401,9 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       // thresholds they update are read again only after the next named barrier.  (After two tiles per CTA the pool
       // already holds the best of ~38k rows; what is admitted later is k * ln(rows / 38k) keys per query over ALL
       // CTAs, so further refreshes are for long scans and drifting corpora only.)
-      if (it == 2 || it == 12 || it == 48 || (it >= 128 && (it & 127) == 0)) {
+      const bool due = k <= kPoolSmallK ? (it == 2 || it == 12 || it == 48 || (it >= 128 && (it & 127) == 0))
+                                        : (it == 2 || it == 4 || it == 8 || it == 16 || it == 32 || (it >= 64 && (it & 63) == 0));
+      if (due) {
         refresh();
         named_bar_sync(1, kEpiThreads);
       }

@@ -143,8 +143,10 @@ def test_bge_large_256_mixed_length_chunks_centred_cosine(dev):
     that centred cosine only stays high if the per-text part of the embedding is right."""
     from comorag_b200.encoder import BertEncoderB200, EncoderConfig, random_state_dict
     cfg = EncoderConfig(1024, 24, 16, 4096, 30522)
-    sd = random_state_dict(cfg, seed=3, std=0.02, device=dev)
-    sd["embeddings.word_embeddings.weight"] = sd["embeddings.word_embeddings.weight"] * 50.0     # std 1.0
+    # layer weights N(0, 0.01), word embeddings N(0, 1): measured on the fp32 oracle, 24 layers of N(0, 0.02) weights
+    # collapse any two texts to cosine 0.92+ whatever the embeddings are; at 0.01 the pair cosine stays near 0.5
+    sd = random_state_dict(cfg, seed=3, std=0.01, device=dev)
+    sd["embeddings.word_embeddings.weight"] = sd["embeddings.word_embeddings.weight"] * 100.0    # std 1.0
     enc = BertEncoderB200(cfg, sd, dev)
     g = torch.Generator().manual_seed(11)
     lens = torch.randint(32, 513, (256,), generator=g).tolist()
