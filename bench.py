@@ -599,6 +599,7 @@ def run_ours(args):
             kernels = ["search_topk_kernel", "merge_topk_kernel" if world == 1 else "finalize_exchange_kernel"]
         else:
             kernels = ["search_topk_kernel", "merge_topk_kernel", "ncclAllGather (library)", "merge_topk_kernel"]
+            use_graph = False
         ours_per_step = sum(1 for kname in kernels if "library" not in kname)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -624,6 +625,9 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        del session
+        index.close()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
     if mism != 0:
         raise SystemExit(f"bench.py: {mism} id mismatches against the float64 ranking -- the timed path returned wrong ids")

@@ -148,7 +148,10 @@ class ShardedIndex:
             elif self.peer is not None:
                 s = SearchSession(self.local, nq, k, exchange=self.peer, world=self.world, use_graph=use_graph)
             else:
-                s = SearchSession(self.local, nq, k, world=self.world, use_graph=use_graph,
+                # NCCL formulation: launched kernel by kernel.  (Capturing the all-gather in a CUDA graph works, but
+                # tearing the process group down while such graphs are alive hung until NCCL's watchdog fired --
+                # measured in round 2 -- so the graph is reserved for the peer-memory formulation.)
+                s = SearchSession(self.local, nq, k, world=self.world, use_graph=False,
                                   gather=lambda out, mine: dist.all_gather_into_tensor(out, mine, group=self.group))
             self._sessions[key] = s
         return s
@@ -175,6 +178,11 @@ class ShardedIndex:
         if len(outs) == 1:
             return outs[0]
         return tuple(torch.cat([o[i] for o in outs], 0) for i in range(3))
+
+    def close(self) -> None:
+        """Drop the captured sessions (call before dist.destroy_process_group())."""
+        with self._lock:
+            self._sessions.clear()
 
     def search(self, queries, k: int):
         """Host-buffer entry point on every rank: numpy / torch queries [nq, dim] in, numpy (ids, scores, minmax) out."""
