@@ -734,7 +734,7 @@ def bench_encode(args, world, rank, dev, st, peaks, barrier, max_over_ranks):
                          "peak_source": peaks["source"] + " (sustained)", "flops_per_chunk": cfg.flops_per_chunk(L)},
             "mixed_length": mixed,
             "probe_batch": {"probes": 32, "tokens_each": 24, "ms": probe_ms, "probes_per_s": 32 / probe_ms * 1e3,
-                            "what": "encode_token_lists through the captured CUDA graph (bucket 2048 tokens), host call to result on device"},
+                            "what": "encode_token_lists through the captured CUDA graph (768-token bucket), host call to result on device"},
             "tokenizer": tok,
             "gpu_launches": args.encode_steps * launches_per_fwd}
 
