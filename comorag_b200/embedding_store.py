@@ -158,16 +158,21 @@ class EmbeddingStore:
     def _append_raw(self, n0: int) -> None:
         import json
         import torch
+        mode = "a"
+        if n0 > 0 and not os.path.exists(self._base + ".meta.json"):
+            # first append over rows that came from somewhere else (a vdb_<ns>.parquet written in parquet mode): the
+            # raw shards must hold EVERY row the meta file is about to vouch for, so write the whole matrix once
+            n0, mode = 0, "w"
         rows = self._host[n0:self._n]
-        with open(self._base + ".rows.jsonl", "a") as f:
+        with open(self._base + ".rows.jsonl", mode) as f:
             for h, t in zip(self.hash_ids[n0:], self.texts[n0:]):
                 f.write(json.dumps({"hash_id": h, "content": t}) + "\n")
-        with open(self._base + ".f32", "ab") as f:
+        with open(self._base + ".f32", mode + "b") as f:
             f.write(np.ascontiguousarray(rows, dtype=np.float32).tobytes())
         dim_pad = (self._dim + 63) // 64 * 64
         padded = torch.zeros((rows.shape[0], dim_pad), dtype=torch.bfloat16)
         padded[:, : self._dim] = torch.from_numpy(np.ascontiguousarray(rows)).to(torch.bfloat16)
-        with open(self._base + ".bf16", "ab") as f:
+        with open(self._base + ".bf16", mode + "b") as f:
             f.write(padded.view(torch.int16).numpy().tobytes())
         # the meta file is the commit record: written last, atomically; a crash before it leaves longer data files,
         # which _load_raw() cuts back to what the meta file vouches for
@@ -234,9 +239,30 @@ class EmbeddingStore:
     # -------------------------------------------------------------- persistence
     def _load_data(self):
         """embedding_store.py:92-107."""
+        if self._persist == "append" and os.path.exists(self._base + ".meta.json") and os.path.exists(self.filename):
+            # both formats present: a parquet file with MORE rows was written later in parquet mode; the raw shards
+            # are stale, so drop their commit record (the next append rewrites them in full) and load the parquet
+            import json
+            import pyarrow.parquet as pq
+            if pq.ParquetFile(self.filename).metadata.num_rows > json.load(open(self._base + ".meta.json")).get("rows", 0):
+                logger.warning(f"{self._base}.*: raw shards are older than {self.filename}; rebuilding them on the next insert")
+                os.remove(self._base + ".meta.json")
         if self._persist == "append" and self._load_raw():
             logger.info(f"Loaded {len(self.hash_ids)} records from {self._base}.* (raw shards)")
             return
+        if self._persist == "parquet" and os.path.exists(self._base + ".meta.json"):
+            # the directory was last written in append-only mode: its raw shards are the truth (a vdb_<ns>.parquet
+            # beside them may be older, or absent); load them and bring the parquet file up to date
+            import json
+            raw_rows = json.load(open(self._base + ".meta.json")).get("rows", 0)
+            pq_rows = -1
+            if os.path.exists(self.filename):
+                import pyarrow.parquet as pq
+                pq_rows = pq.ParquetFile(self.filename).metadata.num_rows
+            if raw_rows > pq_rows and self._load_raw():
+                logger.info(f"Loaded {len(self.hash_ids)} records from {self._base}.* (raw shards newer than the parquet file)")
+                self._save_data()
+                return
         if os.path.exists(self.filename):
             import pyarrow.parquet as pq
             table = pq.read_table(self.filename)

@@ -96,6 +96,14 @@ class DSPyFilter:
         self.global_config = narrtiverag.global_config
         self.embedding_model = getattr(narrtiverag, "embedding_model", None)
         self.cross_encoder = None
+        # The reference's LLM filter returns a SUBSET of the candidates, possibly empty, and ComoRAG falls back to plain
+        # dense retrieval when nothing survives (ComoRAG.py:486-488).  A scorer only orders, so the filtering is made
+        # explicit: candidates scoring below `rerank_score_threshold` (cross-encoder logit, or cosine for the dense
+        # scorer) are dropped, and at most `rerank_keep_fraction` of them are kept.  The defaults keep everything --
+        # with them the empty-facts fallback of the reference can only be reached through an empty candidate list.
+        thr = cfg_get(self.global_config, "rerank_score_threshold", None)
+        self.score_threshold = None if thr is None else float(thr)
+        self.keep_fraction = float(cfg_get(self.global_config, "rerank_keep_fraction", 1.0))
         path = cfg_get(self.global_config, "rerank_model_name", None)
         if path:
             self.cross_encoder = CrossEncoderReranker(
@@ -118,6 +126,10 @@ class DSPyFilter:
         texts = [" ".join(str(x) for x in item) for item in candidate_items]
         scores = self._scores(query, texts)
         order = _order(scores)
+        if self.keep_fraction < 1.0:
+            order = order[: max(0, int(np.ceil(len(order) * self.keep_fraction)))]
+        if self.score_threshold is not None:
+            order = [i for i in order if scores[i] >= self.score_threshold]     # may leave nothing: DPR fallback
         idx = [candidate_indices[i] for i in order][:len_after_rerank]
         items = [candidate_items[i] for i in order][:len_after_rerank]
         return idx, items, {"confidence": [float(scores[i]) for i in order][:len_after_rerank]}

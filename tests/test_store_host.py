@@ -183,3 +183,75 @@ def test_reads_the_parquet_the_reference_wrote(gold, tmp_path):
     import pyarrow.parquet as pq
     ref_schema = pq.read_schema(os.path.join(HERE, "golden", "vdb_chunk_reference.parquet"))
     assert {n: str(ref_schema.field(n).type) for n in ref_schema.names} == gold["parquet_schema"]
+
+
+def test_switching_persistence_modes_keeps_every_row(tmp_path):
+    """parquet -> append-only -> reload, and append-only -> parquet, over the same directory."""
+    import types
+    from comorag_b200.embedding_store import EmbeddingStore
+
+    def model(append):
+        m = types.SimpleNamespace(embedding_dim=8, global_config=types.SimpleNamespace(embedding_store_append_only=append))
+        m.batch_encode = lambda texts, **kw: np.stack([np.full(8, float(len(t)), np.float32) for t in texts])
+        return m
+
+    d = str(tmp_path / "chunk_embeddings")
+    s1 = EmbeddingStore(model(False), d, 4, "chunk")            # reference behaviour: whole-file parquet
+    s1.insert_strings(["a", "bb", "ccc"])
+    s2 = EmbeddingStore(model(True), d, 4, "chunk")             # append-only over the existing parquet
+    assert s2.get_all_ids() == s1.get_all_ids()
+    s2.insert_strings(["dddd", "eeeee"])
+    s3 = EmbeddingStore(model(True), d, 4, "chunk")             # reload from the raw shards: all five rows
+    assert len(s3.get_all_ids()) == 5 and s3.texts == ["a", "bb", "ccc", "dddd", "eeeee"]
+    np.testing.assert_array_equal(s3.get_embeddings(s3.get_all_ids())[:, 0], [1, 2, 3, 4, 5])
+    assert s3.raw_shard_path() is not None
+    s4 = EmbeddingStore(model(False), d, 4, "chunk")            # back to parquet mode: must not lose the appended rows
+    assert s4.texts == s3.texts
+    s4.insert_strings(["ffffff"])
+    s5 = EmbeddingStore(model(False), d, 4, "chunk")
+    assert len(s5.get_all_ids()) == 6 and s5.get_missing_string_hash_ids(["a", "zz"]).keys() == {s5._nodes(["zz"]).popitem()[0]}
+    s6 = EmbeddingStore(model(True), d, 4, "chunk")             # append mode again: the parquet now has one row more
+    assert len(s6.get_all_ids()) == 6
+    s6.insert_strings(["ggggggg"])
+    s7 = EmbeddingStore(model(True), d, 4, "chunk")
+    assert s7.texts[-2:] == ["ffffff", "ggggggg"] and len(s7.get_all_ids()) == 7 and s7.raw_shard_path() is not None
+
+
+def test_sqlite_embedding_cache_round_trip(tmp_path):
+    """make_cache_embed (reference base.py:112-187): rows keyed by (instruction, prompt, max_length); a second call is
+    served from sqlite without touching the encoder, a changed instruction is a different key."""
+    import torch
+    from comorag_b200.embedding_model.base import make_cache_embed
+    calls = []
+
+    def encode(prompts, **kw):
+        calls.append(list(prompts))
+        return torch.tensor([[float(len(p)), float(len(kw.get("instruction", "")))] for p in prompts])
+
+    cached = make_cache_embed(encode, str(tmp_path / "cache.db"), "cpu")
+    a = cached(prompts=["x", "yy"], instruction="I:", max_length=16)
+    b = cached(prompts=["yy", "zzz"], instruction="I:", max_length=16)
+    assert calls == [["x", "yy"], ["zzz"]] and a.shape == (2, 2) and torch.equal(b[0], a[1])
+    c = cached(prompts=["x"], instruction="other", max_length=16)
+    assert calls[-1] == ["x"] and float(c[0, 1]) == 5.0
+    again = make_cache_embed(encode, str(tmp_path / "cache.db"), "cpu")(prompts=["x", "yy", "zzz"], instruction="I:", max_length=16)
+    assert len(calls) == 3 and again[:, 0].tolist() == [1.0, 2.0, 3.0]
+
+
+def test_dspy_filter_can_drop_candidates(tmp_path):
+    """the reference's LLM filter returns a subset, possibly empty (ComoRAG.py:486-488 then falls back to
+    dense retrieval); the scorer-based filter does too once a threshold / keep-fraction is configured."""
+    import types
+    from comorag_b200.rerank import DSPyFilter
+    emb = {"q": [1.0, 0.0], "a b c": [0.9, 0.1], "d e f": [0.2, 0.8], "g h i": [0.5, 0.5]}
+    model = types.SimpleNamespace(batch_encode=lambda texts, **kw: np.array([emb[t] for t in texts], np.float32))
+    items = [("a", "b", "c"), ("d", "e", "f"), ("g", "h", "i")]
+    rag = lambda **cfg: types.SimpleNamespace(global_config=types.SimpleNamespace(**cfg), embedding_model=model)
+    keep_all = DSPyFilter(rag())("q", items, [10, 11, 12], len_after_rerank=5)
+    assert keep_all[0] == [10, 12, 11]
+    thr = DSPyFilter(rag(rerank_score_threshold=0.4))("q", items, [10, 11, 12], len_after_rerank=5)
+    assert thr[0] == [10, 12] and thr[1] == [items[0], items[2]]
+    none = DSPyFilter(rag(rerank_score_threshold=2.0))("q", items, [10, 11, 12], len_after_rerank=5)
+    assert none[0] == [] and none[1] == []
+    half = DSPyFilter(rag(rerank_keep_fraction=0.5))("q", items, [10, 11, 12], len_after_rerank=5)
+    assert half[0] == [10, 12]
