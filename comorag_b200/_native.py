@@ -26,6 +26,9 @@ SIGNATURES = {
     "crag_version": (C.c_int, []),
     "crag_last_error": (C.c_char_p, []),
     "crag_sm_count": (C.c_int, []),
+    "crag_vmem_reserve": (C.c_int, [C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]),
+    "crag_vmem_grow": (C.c_int, [C.c_uint64, C.c_size_t, C.c_size_t]),
+    "crag_vmem_release": (C.c_int, [C.c_uint64, C.c_size_t, C.c_size_t]),
     "crag_search_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "crag_search_topk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

@@ -89,3 +89,114 @@ int sm_count() {
 extern "C" int crag_version(void) { return 1000; }
 extern "C" const char* crag_last_error(void) { return crag::g_err; }
 extern "C" int crag_sm_count(void) { return crag::sm_count(); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Growable device buffer: reserve virtual address space once, map physical memory as the corpus shard grows.
+// The reference keeps its index as a Python list of rows it re-stacks on demand (embedding_store.py:96,147-157); a
+// device shard that reallocates on growth needs old + new storage at once (a 20 GB shard: 50 GB transiently) and moves
+// -- which invalidates every tensor map / captured graph that points at it.  With cuMemAddressReserve + cuMemMap the
+// shard's address never changes and growth copies nothing.
+namespace crag {
+namespace {
+struct VmemApi {
+  CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*addr_free)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  bool ok = false;
+};
+
+const VmemApi& vmem_api() {
+  static VmemApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess;
+    };
+    api.ok = get("cuMemAddressReserve", reinterpret_cast<void**>(&api.reserve)) &&
+             get("cuMemAddressFree", reinterpret_cast<void**>(&api.addr_free)) &&
+             get("cuMemCreate", reinterpret_cast<void**>(&api.create)) &&
+             get("cuMemRelease", reinterpret_cast<void**>(&api.release)) &&
+             get("cuMemMap", reinterpret_cast<void**>(&api.map)) &&
+             get("cuMemUnmap", reinterpret_cast<void**>(&api.unmap)) &&
+             get("cuMemSetAccess", reinterpret_cast<void**>(&api.set_access)) &&
+             get("cuMemGetAllocationGranularity", reinterpret_cast<void**>(&api.granularity));
+  });
+  return api;
+}
+
+CUmemAllocationProp vmem_prop(int dev) {
+  CUmemAllocationProp prop = {};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = dev;
+  return prop;
+}
+}  // namespace
+}  // namespace crag
+
+extern "C" int crag_vmem_reserve(size_t max_bytes, uint64_t* base_out, size_t* granularity_out) {
+  using namespace crag;
+  const VmemApi& api = vmem_api();
+  if (!api.ok) return fail(CRAG_ERR_UNSUPPORTED, "virtual memory management entry points unavailable");
+  if (!base_out || !granularity_out || max_bytes == 0) return fail(CRAG_ERR_INVALID, "crag_vmem_reserve: bad arguments");
+  int dev = 0;
+  CRAG_CUDA_OK(cudaGetDevice(&dev));
+  CRAG_CUDA_OK(cudaFree(nullptr));   // make sure the primary context exists
+  const CUmemAllocationProp prop = vmem_prop(dev);
+  size_t gran = 0;
+  CUresult r = api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED);
+  if (r != CUDA_SUCCESS || gran == 0) return fail(CRAG_ERR_CUDA, "cuMemGetAllocationGranularity failed (%d)", int(r));
+  const size_t size = (max_bytes + gran - 1) / gran * gran;
+  CUdeviceptr base = 0;
+  r = api.reserve(&base, size, gran, 0, 0);
+  if (r != CUDA_SUCCESS) return fail(CRAG_ERR_CUDA, "cuMemAddressReserve(%zu) failed (%d)", size, int(r));
+  *base_out = uint64_t(base);
+  *granularity_out = gran;
+  return CRAG_OK;
+}
+
+extern "C" int crag_vmem_grow(uint64_t base, size_t mapped_bytes, size_t new_mapped_bytes) {
+  using namespace crag;
+  const VmemApi& api = vmem_api();
+  if (!api.ok) return fail(CRAG_ERR_UNSUPPORTED, "virtual memory management entry points unavailable");
+  if (new_mapped_bytes <= mapped_bytes) return CRAG_OK;
+  int dev = 0;
+  CRAG_CUDA_OK(cudaGetDevice(&dev));
+  const CUmemAllocationProp prop = vmem_prop(dev);
+  const size_t bytes = new_mapped_bytes - mapped_bytes;
+  CUmemGenericAllocationHandle h;
+  CUresult r = api.create(&h, bytes, &prop, 0);
+  if (r != CUDA_SUCCESS) return fail(CRAG_ERR_CUDA, "cuMemCreate(%zu) failed (%d): out of device memory?", bytes, int(r));
+  r = api.map(CUdeviceptr(base + mapped_bytes), bytes, 0, h, 0);
+  if (r != CUDA_SUCCESS) {
+    api.release(h);
+    return fail(CRAG_ERR_CUDA, "cuMemMap failed (%d)", int(r));
+  }
+  api.release(h);   // the mapping keeps the memory alive until it is unmapped
+  CUmemAccessDesc acc = {};
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = dev;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  r = api.set_access(CUdeviceptr(base + mapped_bytes), bytes, &acc, 1);
+  if (r != CUDA_SUCCESS) return fail(CRAG_ERR_CUDA, "cuMemSetAccess failed (%d)", int(r));
+  return CRAG_OK;
+}
+
+extern "C" int crag_vmem_release(uint64_t base, size_t mapped_bytes, size_t reserved_bytes) {
+  using namespace crag;
+  const VmemApi& api = vmem_api();
+  if (!api.ok) return fail(CRAG_ERR_UNSUPPORTED, "virtual memory management entry points unavailable");
+  if (mapped_bytes) {
+    CUresult r = api.unmap(CUdeviceptr(base), mapped_bytes);
+    if (r != CUDA_SUCCESS) return fail(CRAG_ERR_CUDA, "cuMemUnmap failed (%d)", int(r));
+  }
+  CUresult r = api.addr_free(CUdeviceptr(base), reserved_bytes);
+  if (r != CUDA_SUCCESS) return fail(CRAG_ERR_CUDA, "cuMemAddressFree failed (%d)", int(r));
+  return CRAG_OK;
+}

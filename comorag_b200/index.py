@@ -24,6 +24,79 @@ def _pad_dim(dim: int) -> int:
     return (dim + 63) // 64 * 64
 
 
+class _GrowableRows:
+    """bf16 [rows, dim_pad] storage whose address never changes: virtual address space reserved once
+    (crag_vmem_reserve), physical memory mapped behind it in `step`-sized pieces as rows arrive (crag_vmem_grow).
+    Growth copies nothing, and tensor maps / captured graphs that point at the shard stay valid."""
+
+    STEP_BYTES = 64 << 20
+
+    def __init__(self, device: torch.device, dim_pad: int, max_bytes: Optional[int] = None):
+        import ctypes as C
+        self.device, self.dim_pad = device, dim_pad
+        self._lib = _native.load()
+        with torch.cuda.device(device):
+            if max_bytes is None:
+                max_bytes = int(torch.cuda.get_device_properties(device).total_memory)
+            base, gran = C.c_uint64(0), C.c_size_t(0)
+            _native.check(self._lib.crag_vmem_reserve(int(max_bytes), C.byref(base), C.byref(gran)), "crag_vmem_reserve")
+        self.base, self.gran = int(base.value), int(gran.value)
+        self.reserved = (int(max_bytes) + self.gran - 1) // self.gran * self.gran
+        self.mapped = 0
+        self._view: Optional[torch.Tensor] = None
+
+    @property
+    def row_bytes(self) -> int:
+        return self.dim_pad * 2
+
+    def capacity_rows(self) -> int:
+        return self.mapped // self.row_bytes
+
+    def ensure_rows(self, rows: int) -> None:
+        need = rows * self.row_bytes
+        if need <= self.mapped:
+            return
+        step = max(self.gran, self.STEP_BYTES // self.gran * self.gran)
+        new = min(self.reserved, (need + step - 1) // step * step)
+        if new < need:
+            raise MemoryError(f"corpus shard would exceed its {self.reserved >> 30} GiB address reservation")
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.crag_vmem_grow(self.base, self.mapped, new), "crag_vmem_grow")
+        # fresh pages: zero them once so the dim..dim_pad padding columns read as 0
+        fresh = self._alias(self.mapped, new - self.mapped)
+        fresh.zero_()
+        self.mapped = new
+        self._view = None
+
+    def _alias(self, offset: int, nbytes: int) -> torch.Tensor:
+        holder = type("_Mem", (), {"__cuda_array_interface__": {
+            "shape": (nbytes // 2,), "typestr": "<i2", "data": (self.base + offset, False), "version": 3, "strides": None}})()
+        holder.owner = self        # torch keeps the holder alive for the tensor's lifetime: so the mapping outlives every alias
+        return torch.as_tensor(holder, device=self.device)
+
+    def tensor(self) -> torch.Tensor:
+        """bf16 [capacity_rows, dim_pad] view of everything mapped so far (same address after every growth)."""
+        if self._view is None:
+            rows = self.capacity_rows()
+            self._view = self._alias(0, rows * self.row_bytes).view(torch.bfloat16).view(rows, self.dim_pad) if rows else \
+                torch.zeros((0, self.dim_pad), dtype=torch.bfloat16, device=self.device)
+        return self._view
+
+    def close(self) -> None:
+        if self.base:
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize(self.device)
+                self._view = None
+                self._lib.crag_vmem_release(self.base, self.mapped, self.reserved)
+            self.base, self.mapped = 0, 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DenseIndex:
     """One corpus shard in HBM.
 
@@ -31,7 +104,8 @@ class DenseIndex:
     index owns ids [row_offset, row_offset + n_rows)).
     """
 
-    def __init__(self, dim: int, device: Optional[torch.device] = None, capacity: int = 0, row_offset: int = 0):
+    def __init__(self, dim: int, device: Optional[torch.device] = None, capacity: int = 0, row_offset: int = 0,
+                 _adopt: Optional[torch.Tensor] = None):
         if dim < 1:
             raise ValueError("dim must be positive")
         self.dim = int(dim)
@@ -45,9 +119,17 @@ class DenseIndex:
         self.device = torch.device(device)
         self.row_offset = int(row_offset)
         self._n = 0
-        self._buf = torch.zeros((max(int(capacity), 0), self.dim_pad), dtype=torch.bfloat16, device=self.device)
-        self._lock = threading.Lock()
         _native.load()
+        # rows appended with add() live behind a fixed virtual address and grow without reallocation (_GrowableRows);
+        # from_tensor() adopts a caller's tensor instead
+        self._rows: Optional[_GrowableRows] = None
+        if _adopt is not None:
+            self._buf = _adopt
+        else:
+            self._rows = _GrowableRows(self.device, self.dim_pad)
+            self._rows.ensure_rows(max(int(capacity), 0))
+            self._buf = self._rows.tensor()
+        self._lock = threading.Lock()
 
     # ------------------------------------------------------------------ build
     @classmethod
@@ -57,8 +139,7 @@ class DenseIndex:
             raise ValueError("from_tensor expects a CUDA bf16 [n, dim] tensor")
         if rows.shape[1] % 64 != 0 or rows.stride(1) != 1 or rows.stride(0) % 8 != 0:
             raise ValueError("from_tensor needs dim % 64 == 0 and a row stride that is a multiple of 8")
-        self = cls(rows.shape[1], device=rows.device, row_offset=row_offset)
-        self._buf = rows
+        self = cls(rows.shape[1], device=rows.device, row_offset=row_offset, _adopt=rows)
         self._n = rows.shape[0]
         return self
 
@@ -81,10 +162,14 @@ class DenseIndex:
     def _reserve(self, n: int) -> None:
         if n <= self._buf.shape[0]:
             return
-        cap = max(n, int(self._buf.shape[0] * 1.5) + 1024)
-        new = torch.zeros((cap, self.dim_pad), dtype=torch.bfloat16, device=self.device)
-        new[: self._n] = self._buf[: self._n]
-        self._buf = new
+        if self._rows is None:
+            # an adopted tensor (from_tensor) that now has to grow: move it behind a growable reservation once
+            self._rows = _GrowableRows(self.device, self.dim_pad)
+            self._rows.ensure_rows(n)
+            self._rows.tensor()[: self._n] = self._buf[: self._n]
+        else:
+            self._rows.ensure_rows(n)       # maps more pages behind the same address; nothing is copied
+        self._buf = self._rows.tensor()
 
     def add(self, vectors) -> None:
         """Append rows (numpy / torch, any float dtype, [n, dim]); stored as bf16."""

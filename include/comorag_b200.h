@@ -52,6 +52,16 @@ CRAG_API const char* crag_last_error(void);
 /* Number of SMs of the current device (148 on B200); <0 on error. */
 CRAG_API int crag_sm_count(void);
 
+/* Growable device buffer for a corpus shard that is appended to (EmbeddingStore.insert_strings, embedding_store.py:63-90):
+ * virtual address space is reserved once, physical memory is mapped behind it as rows arrive, so growth neither copies
+ * the shard nor moves it (tensor maps and captured graphs stay valid).  Sizes are multiples of *granularity_out.
+ *   crag_vmem_reserve  reserve >= max_bytes of address space on the current device -> base address, granularity
+ *   crag_vmem_grow     back [mapped_bytes, new_mapped_bytes) of that range with device memory (read/write)
+ *   crag_vmem_release  unmap [0, mapped_bytes) and free the reservation (caller has synchronised the device) */
+CRAG_API int crag_vmem_reserve(size_t max_bytes, uint64_t* base_out, size_t* granularity_out);
+CRAG_API int crag_vmem_grow(uint64_t base, size_t mapped_bytes, size_t new_mapped_bytes);
+CRAG_API int crag_vmem_release(uint64_t base, size_t mapped_bytes, size_t reserved_bytes);
+
 /* ------------------------------------------------------------------ search
  * Fused brute-force inner-product top-k over one corpus shard.
  *

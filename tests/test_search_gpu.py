@@ -426,3 +426,46 @@ def test_fused_finalize_exchange_merge_virtual_ranks(dev, world, k):
         for r in range(world):
             sessions[r].exchange.check()
             assert torch.equal(outs[r][0], want[0]) and torch.equal(outs[r][1], want[1]) and torch.equal(outs[r][2], want[2]), (epoch, r)
+
+
+def test_dense_index_save_load_round_trip(dev, tmp_path):
+    """DenseIndex.save / load (per-rank raw bf16 shard + json meta): rows, row_offset and search results survive."""
+    from comorag_b200.index import DenseIndex
+    rows = make_unit_rows(3000, 100, 12, device=dev)           # dim 100 -> padded to 128 in the shard
+    idx = DenseIndex(100, device=dev, row_offset=5000)
+    idx.add(rows)
+    path = str(tmp_path / "shard.bf16")
+    idx.save(path)
+    back = DenseIndex.load(path, device=dev)
+    assert back.n_rows == 3000 and back.dim == 100 and back.row_offset == 5000
+    assert torch.equal(back.matrix(), idx.matrix())
+    q = make_unit_rows(5, 100, 13).float().numpy()
+    a, b = idx.search(q, 10), back.search(q, 10)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and a[0].min() >= 5000
+
+
+def test_shard_grows_in_place_without_moving(dev):
+    """DenseIndex.add() over a virtual-address reservation: the shard's address is the same after every growth (no
+    reallocation, no copy), appended rows are searchable, padding columns stay zero, and device memory in use rises
+    by about the shard's size, not a multiple of it."""
+    from comorag_b200.index import DenseIndex
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(dev)
+    idx = DenseIndex(100, device=dev)                      # dim 100 -> 128 columns
+    ptrs, total = set(), 0
+    rows = make_unit_rows(300_000, 100, 21, device=dev)
+    for s0 in range(0, 300_000, 50_000):
+        idx.add(rows[s0:s0 + 50_000])
+        total += 50_000
+        ptrs.add(idx._buf.data_ptr())
+        assert idx.n_rows == total
+    assert len(ptrs) == 1, "the shard moved while growing"
+    assert torch.equal(idx.matrix(), rows) and float(idx._buf[:total, 100:].abs().max()) == 0.0
+    want = DenseIndex.from_tensor(torch.nn.functional.pad(rows, (0, 28)).contiguous()).search_device(
+        torch.nn.functional.pad(make_unit_rows(4, 100, 22, device=dev), (0, 28)).contiguous(), 10)
+    got = idx.search_device(torch.nn.functional.pad(make_unit_rows(4, 100, 22, device=dev), (0, 28)).contiguous(), 10)
+    assert all(torch.equal(a, b) for a, b in zip(got, want))
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(dev)
+    shard_bytes = 300_000 * 128 * 2
+    assert free0 - free1 < 3 * shard_bytes + (256 << 20)   # the shard (+ its 64 MB growth step, + test tensors), not 2.5x of it
