@@ -124,9 +124,10 @@ def test_unmodified_comorag_search_half_on_the_device_matches_the_reference_rank
     assert summary["queries"] == n >= 9
     # every tri_retrieve went through a retrieval wave: per wave one score-all pass over each of the fact / passage /
     # summary shards and one fused top-k pass over the timeline shard; per query two device rankings
-    waves = got["wave_stats"]["waves"]
-    assert got["wave_stats"]["queries"] == n and 1 <= waves <= n
-    assert calls["scores"] >= 3 * waves and calls["rank"] >= 2 * n and calls["topk"] >= waves
+    # (a probe string that repeats across questions is served from the wave's parked results: queries <= n)
+    waves, served = got["wave_stats"]["waves"], got["wave_stats"]["queries"]
+    assert 1 <= waves <= served <= n and served >= n - 3
+    assert calls["scores"] >= 3 * waves and calls["rank"] >= 2 * served and calls["topk"] >= waves
 
 
 @needs_ref
@@ -154,9 +155,10 @@ def test_unmodified_comorag_runs_on_the_shim_and_retrieves_what_the_reference_re
     assert summary["queries"] == n >= 9
     # every tri_retrieve ran on the device kernels, shared by the concurrent questions (one wave = one encode + one
     # pass per shard); retrieve_knn added fused top-k passes at index time
-    waves = got["wave_stats"]["waves"]
-    assert got["wave_stats"]["queries"] == n and 1 <= waves <= n
-    assert calls["scores"] >= 3 * waves and calls["rank"] >= 2 * n and calls["topk"] >= waves
+    # (a probe string that repeats across questions is served from the wave's parked results: queries <= n)
+    waves, served = got["wave_stats"]["waves"], got["wave_stats"]["queries"]
+    assert 1 <= waves <= served <= n and served >= n - 3
+    assert calls["scores"] >= 3 * waves and calls["rank"] >= 2 * served and calls["topk"] >= waves
     # and the per-character encode waste is gone: one encoded text per tri_retrieve instead of 2 * len(query) + 4
     assert got["query_encodes"]["encoded_texts"] <= n + 16 * 3
     assert ref["query_encodes"]["encoded_texts"] > 5 * got["query_encodes"]["encoded_texts"]
