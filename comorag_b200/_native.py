@@ -64,6 +64,8 @@ SIGNATURES = {
     "crag_search_finalize_exchange": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_void_p,
                                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]),
+    "crag_ivf_assign": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "crag_search_scores": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "crag_rank_workspace_bytes": (C.c_size_t, [C.c_int64]),

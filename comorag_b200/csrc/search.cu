@@ -197,6 +197,12 @@ struct NoIvfArgs {};
 struct ScoreArgs {
   float* out;
   int64_t ld;
+  // assignment mode (best_id != nullptr): instead of storing the scores, each row keeps the running argmax over the
+  // query blocks it has met -- the IVF build's "which centroid does this row belong to" (rows = corpus, centroids =
+  // queries, 32 per pass).  A row is owned by one thread per pass and passes are stream-ordered: plain read-modify-write.
+  float* best_score;
+  int32_t* best_id;
+  int32_t base_id;
 };
 template <bool IVF, bool SCORES> struct IvfParam { using type = NoIvfArgs; };
 template <> struct IvfParam<true, false> { using type = IvfArgs; };
@@ -420,12 +426,25 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
       if constexpr (SCORES) {
         const int srow = tile * kTileRows + quad * 32 + lane;
         if (srow < n_rows) {
+          if (ivf.best_id != nullptr) {
+            const bool first = ivf.base_id == 0;       // the first centroid block starts every row's running best
+            float bs = first ? -INFINITY : ivf.best_score[srow];
+            int32_t bi = first ? 0 : ivf.best_id[srow];
 #pragma unroll
-          for (int q = 0; q < kNQ; ++q) {
-            const float s = __uint_as_float(r[q]);
-            mn[q] = fminf(mn[q], s);
-            mx[q] = fmaxf(mx[q], s);
-            if (q < nq) ivf.out[int64_t(q) * ivf.ld + srow] = s;
+            for (int q = 0; q < kNQ; ++q) {
+              const float s = __uint_as_float(r[q]);
+              if (q < nq && s > bs) { bs = s; bi = ivf.base_id + q; }   // strict: ties stay with the smaller id
+            }
+            ivf.best_score[srow] = bs;
+            ivf.best_id[srow] = bi;
+          } else {
+#pragma unroll
+            for (int q = 0; q < kNQ; ++q) {
+              const float s = __uint_as_float(r[q]);
+              mn[q] = fminf(mn[q], s);
+              mx[q] = fmaxf(mx[q], s);
+              if (q < nq) ivf.out[int64_t(q) * ivf.ld + srow] = s;
+            }
           }
         }
         continue;
@@ -1302,7 +1321,7 @@ extern "C" int crag_search_scores(const void* corpus, int64_t n_rows, int dim, i
     CUtensorMap tm_q;
     rc = make_tmap_bf16_2d(&tm_q, static_cast<const uint8_t*>(queries) + size_t(q0) * dim * 2, uint64_t(nqc), uint64_t(dim), uint64_t(dim) * 2, kNQ);
     if (rc != CRAG_OK) return rc;
-    ScoreArgs sa{out_scores + int64_t(q0) * out_ld, out_ld};
+    ScoreArgs sa{out_scores + int64_t(q0) * out_ld, out_ld, nullptr, nullptr, 0};
     kern<<<grid, kSearchThreads, smem, stream>>>(tm_corpus, tm_q, int(n_rows), num_kb, nqc, 1, nullptr, nullptr, 0u, 0, nullptr,
                                                  part_minmax, sa);
     CRAG_CUDA_OK(cudaGetLastError());
@@ -1340,5 +1359,43 @@ extern "C" int crag_search_finalize_exchange(const void* workspace, size_t works
   else
     finalize_exchange_kernel<128, 128><<<nq, 128, 0, stream>>>(part_keys, part_minmax, parts, nq, k, row_offset, peer_bufs, rank, world, epochs, status, out_ids, out_scores, out_minmax);
   CRAG_CUDA_OK(cudaGetLastError());
+  return CRAG_OK;
+}
+
+// IVF build, assignment step: list of every row = argmax over the centroid table of bf16(row) . bf16(centroid) with fp32
+// accumulation, ties to the smaller list id (oracle/ivf_oracle.py `assign`).  The rows are the "corpus" of the scan
+// kernel and the centroids its query blocks (32 per pass): nlist / 32 passes over the rows, each row keeping its
+// running best in (best_score, best_id).  Replaces a torch matmul + argmax over [rows, nlist] score blocks.
+extern "C" int crag_ivf_assign(const void* rows, int64_t n_rows, int dim, int64_t row_stride, const void* centroids,
+                               int nlist, float* best_score, int32_t* best_id, void* workspace, size_t workspace_bytes,
+                               crag_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const SearchPlan plan = plan_search(1);
+  int rc = check_search_args(rows, n_rows, dim, row_stride, centroids, nlist, 1, workspace, workspace_bytes, plan);
+  if (rc != CRAG_OK) return rc;
+  if (!best_score || !best_id) return fail(CRAG_ERR_INVALID, "crag_ivf_assign: null output pointer");
+  const int grid = scan_grid(n_rows, plan);
+  if (grid == 0) return CRAG_OK;
+  float* part_minmax = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plan.keys_bytes);
+  CUtensorMap tm_rows;
+  rc = make_tmap_bf16_2d(&tm_rows, rows, uint64_t(n_rows), uint64_t(dim), uint64_t(row_stride) * 2, kTileRows);
+  if (rc != CRAG_OK) return rc;
+  const int num_kb = dim / kBlockK;
+  using L = SearchLayout<16, 16, 9>;
+  auto kern = search_topk_kernel<16, 16, 9, false, true>;
+  const size_t smem = L::smem_bytes(num_kb);
+  rc = ensure_smem_attr<KernelTag<16, 16, 9, false, true>>(kern, smem);
+  if (rc != CRAG_OK) return rc;
+  // the pass over centroid block 0 initialises every row's running best (-inf, list 0); later passes update it
+  for (int q0 = 0; q0 < nlist; q0 += kNQ) {
+    const int nqc = (nlist - q0) < kNQ ? (nlist - q0) : kNQ;
+    CUtensorMap tm_q;
+    rc = make_tmap_bf16_2d(&tm_q, static_cast<const uint8_t*>(centroids) + size_t(q0) * dim * 2, uint64_t(nqc), uint64_t(dim), uint64_t(dim) * 2, kNQ);
+    if (rc != CRAG_OK) return rc;
+    ScoreArgs sa{nullptr, 0, best_score, best_id, q0};
+    kern<<<grid, kSearchThreads, smem, stream>>>(tm_rows, tm_q, int(n_rows), num_kb, nqc, 1, nullptr, nullptr, 0u, 0, nullptr,
+                                                 part_minmax, sa);
+    CRAG_CUDA_OK(cudaGetLastError());
+  }
   return CRAG_OK;
 }

@@ -13,8 +13,9 @@ every list padded to whole 128-row tiles so that a tile belongs to exactly one l
     row_ids     int64 [total_tiles * 128]               original id of a stored row, -1 for padding
     list_tile_start int32 [nlist + 1], list_rows int32 [nlist]
 
-Index BUILD (k-means + assignment) runs on the device with torch matmul / argmax / index_add -- build is plumbing
-around the search path here, not a hand-written kernel yet; SEARCH is the C-ABI call.
+Index BUILD: the assignment of rows to centroids (k-means iterations and the final pass) is crag_ivf_assign -- the scan
+kernel with the rows as corpus and the centroid table as its query blocks; the centroid update and the counting sort
+by list are torch index arithmetic (bookkeeping).  SEARCH is crag_ivf_search.
 """
 from __future__ import annotations
 
@@ -50,24 +51,45 @@ def ivf_layout(assignment: torch.Tensor, nlist: int) -> Tuple[torch.Tensor, torc
     return order, dest, tile_start.to(torch.int32), counts.to(torch.int32)
 
 
+def assign_device(rows_bf16: torch.Tensor, centroids_bf16: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """crag_ivf_assign: (list id int32 [n], best inner product fp32 [n]) of every bf16 row against the bf16 centroid
+    table -- nlist / 32 passes of the scan kernel over the rows, no [rows, nlist] score matrix, no library GEMM."""
+    lib = _native.load()
+    n, dim = rows_bf16.shape
+    dev = rows_bf16.device
+    c = centroids_bf16.contiguous()
+    with torch.cuda.device(dev):
+        best = torch.empty(n, dtype=torch.float32, device=dev)
+        ids = torch.empty(n, dtype=torch.int32, device=dev)
+        ws_bytes = lib.crag_search_workspace_bytes(32, 1)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        rc = lib.crag_ivf_assign(rows_bf16.data_ptr(), n, dim, rows_bf16.stride(0), c.data_ptr(), c.shape[0],
+                                 best.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws_bytes,
+                                 torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(rc, "crag_ivf_assign")
+    return ids, best
+
+
 def spherical_kmeans(x: torch.Tensor, nlist: int, iters: int = 10, seed: int = 0, block: int = 1 << 18) -> torch.Tensor:
-    """Lloyd on the unit sphere, on x's device: assign by largest inner product, centroid = normalised mean; an
-    empty list is re-seeded from the rows worst served by their centroid.  fp32 [nlist, dim]."""
+    """Lloyd on the unit sphere, on x's device: assign by largest inner product (crag_ivf_assign over the bf16 sample
+    and the current bf16 centroids), centroid = normalised mean of its rows (index_add: bookkeeping, not arithmetic
+    worth a kernel); an empty list is re-seeded from the rows worst served by their centroid.  fp32 [nlist, dim]."""
     n, dim = x.shape
     if not 1 <= nlist <= n:
         raise ValueError("need 1 <= nlist <= rows")
     g = torch.Generator(device=x.device).manual_seed(seed)
     c = x[torch.randperm(n, generator=g, device=x.device)[:nlist]].float().clone()
+    xb16 = x.to(torch.bfloat16).contiguous()
     for _ in range(iters):
         sums = torch.zeros((nlist, dim), dtype=torch.float32, device=x.device)
         counts = torch.zeros(nlist, dtype=torch.float32, device=x.device)
-        best = torch.empty(n, dtype=torch.float32, device=x.device)
+        a_all, best = assign_device(xb16, c.to(torch.bfloat16))
+        a_all = a_all.to(torch.int64)
         for s in range(0, n, block):
             xb = x[s:s + block].float()
-            sc, a = (xb @ c.T).max(dim=1)
-            best[s:s + block] = sc
+            a = a_all[s:s + block]
             sums.index_add_(0, a, xb)
-            counts.index_add_(0, a, torch.ones_like(sc))
+            counts.index_add_(0, a, torch.ones_like(best[s:s + block]))
         empty = torch.nonzero(counts == 0).flatten()
         if empty.numel():
             worst = torch.topk(best, int(empty.numel()), largest=False).indices
@@ -76,12 +98,13 @@ def spherical_kmeans(x: torch.Tensor, nlist: int, iters: int = 10, seed: int = 0
     return c
 
 
-def assign_rows(x: torch.Tensor, centroids_bf16: torch.Tensor, block: int = 1 << 18) -> torch.Tensor:
-    """argmax_l bf16(x) . bf16(c_l) with fp32 accumulation, ties to the smaller list id; int64 [n]."""
-    cf = centroids_bf16.float()
+def assign_rows(x: torch.Tensor, centroids_bf16: torch.Tensor, block: int = 1 << 22) -> torch.Tensor:
+    """argmax_l bf16(x) . bf16(c_l) with fp32 accumulation, ties to the smaller list id; int64 [n].  The rows go through
+    crag_ivf_assign in blocks (the bf16 copy of a block is the only temporary)."""
     out = torch.empty(x.shape[0], dtype=torch.int64, device=x.device)
     for s in range(0, x.shape[0], block):
-        out[s:s + block] = (x[s:s + block].to(torch.bfloat16).float() @ cf.T).argmax(dim=1)
+        ids, _ = assign_device(x[s:s + block].to(torch.bfloat16).contiguous(), centroids_bf16)
+        out[s:s + block] = ids
     return out
 
 

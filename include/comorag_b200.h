@@ -222,6 +222,14 @@ CRAG_API int crag_ivf_search(const void* residuals, int64_t n_rows_padded, int d
                              int64_t* out_ids, float* out_scores, float* out_minmax, void* workspace,
                              size_t workspace_bytes, crag_stream_t stream);
 
+/* IVF build, assignment step: best_id[r] = argmax_l bf16(row r) . bf16(centroid l) (fp32 accumulation on the tensor
+ * cores, ties to the smaller l), best_score[r] = that inner product.  rows device bf16 [n_rows, dim] (row_stride
+ * elements), centroids device bf16 [nlist, dim] contiguous; outputs device fp32 / int32 [n_rows].  nlist / 32 passes of
+ * the scan kernel over the rows (centroids are its query blocks).  Workspace as crag_search_topk(nq = 32, k = 1). */
+CRAG_API int crag_ivf_assign(const void* rows, int64_t n_rows, int dim, int64_t row_stride, const void* centroids,
+                             int nlist, float* best_score, int32_t* best_id, void* workspace, size_t workspace_bytes,
+                             crag_stream_t stream);
+
 /* Encoder weights (BERT-family, post-LN; HF BertModel parameter names in
  * comments).  Matrices are device bf16 in torch.nn.Linear layout [out, in];
  * biases and LayerNorm parameters are device fp32.  The struct itself and the
