@@ -180,10 +180,16 @@ class RetrievalWave:
         return [by_query[q] for q in queries]
 
 
+_wave_create_lock = __import__("threading").Lock()
+
+
 def _wave(self):
     w = getattr(self, "_crag_wave", None)
     if w is None and getattr(self.global_config, "retrieval_wave", True) and isinstance(getattr(self, "fact_embeddings", None), ShardMatrix):
-        w = self._crag_wave = RetrievalWave(self)
+        with _wave_create_lock:      # up to 16 threads reach their first tri_retrieve together (ComoRAG.py:436-441)
+            w = getattr(self, "_crag_wave", None)
+            if w is None:
+                w = self._crag_wave = RetrievalWave(self)
     return w
 
 
