@@ -45,7 +45,8 @@ constexpr uint32_t kTmemCols = kAccStages * kNQ;  // 512 columns = all of TMEM (
 // largest of ITS query in registers (no cross-lane traffic at all), and the floor is the minimum over the four warps
 // of their kp-th largest: every quarter of the CTAs then holds kp rows at or above it, i.e. at least k shard rows
 // reach the floor and no row with a smaller key can rank in the top-k.  For larger k (after tiles 2, 4, 8, 16, 32
-// and every 64th): the warp owning a query finds the k-th largest of ALL pooled keys by bisection (pooled_kth_key).  All CTAs thus work with (almost) the global k-th best seen so far
+// and every 64th): the k-th largest of the CTAs' BEST keys by bisection, the eight queries a warp owns together
+// (pooled_floor_batch8); only when k exceeds 0.8 x the CTA count do all four keys per CTA enter (pooled_kth_key).  All CTAs thus work with (almost) the global k-th best seen so far
 // instead of their private one.  This replaces the separate sample pre-pass of round 1 (two launches fewer), cuts
 // admissions at k = 100 by about two orders of magnitude, and -- because the floor is a full key, row id included --
 // keeps tie-heavy corpora (duplicate rows) from flooding the selector with rows that only tie the k-th score.
@@ -155,6 +156,76 @@ __device__ __forceinline__ uint64_t pooled_kth_key(const uint64_t* __restrict__ 
     }
   }
   return kth_largest_key<NV>(hi, lo, k);
+}
+
+// The usual refresh (k <= 0.8 * CTAs): only each CTA's BEST key is pooled -- the k-th largest of ~148 CTA maxima is
+// within a factor ~1.6 in admission rate of the true k-th best of everything seen, because k < #CTAs -- and a select
+// warp bisects the floors of ALL EIGHT queries it owns at once: the eight bisections are independent, so their
+// warp reductions pipeline instead of costing one full REDUX latency per step and query (measured before: 3.3 us per
+// query done one after the other, 26 us per warp and refresh; the lane-per-query variant of GPU call 6 was fine at
+// k = 10 but needed k / 4 registers per lane and spilled at k = 100).
+__device__ __forceinline__ void pooled_floor_batch8(const uint64_t* __restrict__ pool, int n_ctas, int ew, int nq,
+                                                    int k, int lane, uint64_t (&out)[8]) {
+  constexpr int NC = kPoolMaxCtas / 32;
+  uint32_t hi[8][NC], lo[8][NC];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int q = ew + 4 * j;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int c = lane + 32 * i;
+      const uint64_t x = (q < nq && c < n_ctas) ? __ldcg(pool + (size_t(c) * kPoolM) * kNQ + q) : 0ull;
+      lo[j][i] = uint32_t(x);
+      hi[j][i] = uint32_t(x >> 32);
+    }
+  }
+  uint32_t t[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t[j] = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    int cnt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t cand = t[j] | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) c += (hi[j][i] >= cand) ? 1 : 0;
+      cnt[j] = c;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (__reduce_add_sync(0xffffffffu, cnt[j]) >= k) t[j] |= (1u << bit);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    out[j] = 0ull;
+    if (t[j] == 0u) continue;          // fewer than k CTAs have published for this query (warp-uniform)
+    int c_gt = 0, c_eq = 0;
+    uint32_t lo_min = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      c_gt += (hi[j][i] > t[j]) ? 1 : 0;
+      if (hi[j][i] == t[j]) { ++c_eq; lo_min = lo[j][i] < lo_min ? lo[j][i] : lo_min; }
+    }
+    c_gt = __reduce_add_sync(0xffffffffu, c_gt);
+    c_eq = __reduce_add_sync(0xffffffffu, c_eq);
+    const int need = k - c_gt;
+    if (need >= c_eq) {
+      out[j] = (uint64_t(t[j]) << 32) | __reduce_min_sync(0xffffffffu, lo_min);
+    } else {                            // ties at the k-th score (duplicate rows): bisect the row word among them
+      uint32_t l = 0;
+#pragma unroll 1
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = l | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) c += (hi[j][i] == t[j] && lo[j][i] >= cand) ? 1 : 0;
+        if (__reduce_add_sync(0xffffffffu, c) >= need) l = cand;
+      }
+      out[j] = (uint64_t(t[j]) << 32) | l;
+    }
+  }
 }
 
 template <int KLIST, int CAP, int STAGES>
@@ -384,6 +455,14 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
 #pragma unroll
           for (int w2 = 1; w2 < 4; ++w2) pf = part_floor[w2 * kNQ + q] < pf ? part_floor[w2 * kNQ + q] : pf;
           raise_to(q, pf);
+        }
+      } else if (5 * k <= 4 * int(gridDim.x)) {
+        // k below the CTA count: the CTAs' best keys suffice; this warp's eight queries are bisected together
+        uint64_t pf[8];
+        pooled_floor_batch8(pool, int(gridDim.x), ew, nq, k, lane, pf);
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) raise_to(ew + 4 * j, pf[j]);
         }
       } else {
         for (int q = ew; q < nq; q += 4) {
