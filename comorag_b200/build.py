@@ -26,6 +26,9 @@ NVCC_FLAGS = [
 ]
 
 
+LAST_BUILD_MODE = "not built in this process"
+
+
 def _nvcc() -> str:
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(exe):
@@ -47,8 +50,11 @@ def _stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every csrc/*.cu into one shared library; returns its path."""
+    global LAST_BUILD_MODE
     if not force and not _stale():
+        LAST_BUILD_MODE = "up-to-date (every csrc/*.cu, *.cuh and include/*.h is older than the .so)"
         return LIB_PATH
+    LAST_BUILD_MODE = "compiled with nvcc -gencode arch=compute_100a,code=sm_100a"
     LIB_DIR.mkdir(parents=True, exist_ok=True)
     objs = []
     obj_dir = LIB_DIR / "obj"

@@ -7,11 +7,14 @@
 // masked mean.
 //
 //   embed_layernorm   word+position+token_type(0) embedding gather + LayerNorm
-//   layernorm         LayerNorm of (GEMM-out + bias + residual), fused in the
-//                     GEMM epilogue, fp32 statistics, bf16 in/out
+//   layernorm         LayerNorm as its OWN pass over the [T, H] activation the
+//                     residual GEMM wrote (bias + residual are fused in that
+//                     GEMM's epilogue, the normalisation is not: a row spans
+//                     four 256-column GEMM tiles); fp32 statistics, bf16 in/out
 //   attention         varlen multi-head self-attention, flash-style online
-//                     softmax, mma.sync m16n8k16 bf16 tiles (round-1 kernel; the
-//                     GEMMs carry ~92% of the flops and run on tcgen05)
+//                     softmax, mma.sync m16n8k16 bf16 tiles: head dim 32
+//                     (bge-small) only -- head dim 64 runs attention_tc.cu on
+//                     tcgen05
 //   pool_normalize    K3: masked mean over tokens + L2 normalise, writes fp32
 //                     [n, H] for the host API and (optionally) the bf16 row
 //                     straight into the corpus shard

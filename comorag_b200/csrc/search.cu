@@ -19,7 +19,15 @@
 //            min/max in registers and offers scores that beat the query's
 //            current k-th best to a small shared candidate buffer; full
 //            buffers are bitonic-sorted in registers by one warp (topk.cuh).
+//            The admission threshold is the better of the CTA's own k-th key
+//            and a floor pooled over ALL CTAs (kPoolM below).
 // The shard is read exactly once from HBM: algorithmic bytes = n_rows*dim*2.
+// Variants of the same pipeline: IVF = true walks a work-list of probed tiles
+// (crag_ivf_search); SCORES = true stores every score (crag_search_scores) or
+// keeps each row's running argmax over centroid blocks (crag_ivf_assign).
+// Around it in this file: the per-shard merge (merge_topk_kernel), the fused
+// finalize + NVLink exchange + global merge of the row-sharded index
+// (finalize_exchange_kernel), and the C-ABI entry points.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "topk.cuh"

@@ -4,7 +4,7 @@
 #   2. --set full capture of the dominant kernel (search scan) and of the encoder GEMMs / attention
 set -u
 mkdir -p gpurun_out
-K='regex:search_topk_kernel|merge_topk_kernel|gemm2?_bf16_kernel|attention_(tc_)?kernel|layernorm_kernel|pool_normalize_kernel'
+K='regex:search_topk_kernel|merge_topk_kernel|finalize_exchange_kernel|hist_kernel|scan_kernel|scatter_kernel|gemm2?_bf16_kernel|attention_(tc_)?kernel|layernorm_kernel|pool_normalize_kernel'
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 600 --csv \
     --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --encode-steps 1 --no-cpu-baseline \
     > gpurun_out/launches_bench.log 2>&1
