@@ -59,6 +59,7 @@ constexpr uint32_t kTmemCols = kAccStages * kNQ;  // 512 columns = all of TMEM (
 // admissions at k = 100 by about two orders of magnitude, and -- because the floor is a full key, row id included --
 // keeps tie-heavy corpora (duplicate rows) from flooding the selector with rows that only tie the k-th score.
 constexpr int kPoolM = 4;
+constexpr int kPoolSlots = kPoolM + 1;   // + slot kPoolM: the CTA's OWN k-th key (0 until its list is full)
 constexpr int kPoolMaxCtas = 160;
 constexpr int kPoolSmallK = 16;     // up to this k only each CTA's BEST key is pooled (37 CTA maxima per warp decide)
 
@@ -85,7 +86,7 @@ __device__ __forceinline__ uint64_t lane_kth_of_pool(const uint64_t* __restrict_
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int c = c0 + 4 * u;
-        v[u] = c < n_ctas ? __ldcg(pool + (size_t(c) * kPoolM) * kNQ + q) : 0ull;
+        v[u] = c < n_ctas ? __ldcg(pool + (size_t(c) * kPoolSlots) * kNQ + q) : 0ull;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) offer(v[u]);
@@ -96,7 +97,7 @@ __device__ __forceinline__ uint64_t lane_kth_of_pool(const uint64_t* __restrict_
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int c = c0 + 4 * (u / kPoolM);
-        v[u] = c < n_ctas ? __ldcg(pool + (size_t(c) * kPoolM + (u % kPoolM)) * kNQ + q) : 0ull;
+        v[u] = c < n_ctas ? __ldcg(pool + (size_t(c) * kPoolSlots + (u % kPoolM)) * kNQ + q) : 0ull;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) offer(v[u]);
@@ -158,7 +159,7 @@ __device__ __forceinline__ uint64_t pooled_kth_key(const uint64_t* __restrict__ 
     const int c = lane + 32 * i;
 #pragma unroll
     for (int m = 0; m < kPoolM; ++m) {
-      const uint64_t x = c < n_ctas ? __ldcg(pool + (size_t(c) * kPoolM + m) * kNQ + q) : 0ull;
+      const uint64_t x = c < n_ctas ? __ldcg(pool + (size_t(c) * kPoolSlots + m) * kNQ + q) : 0ull;
       lo[kPoolM * i + m] = uint32_t(x);
       hi[kPoolM * i + m] = uint32_t(x >> 32);
     }
@@ -172,8 +173,11 @@ __device__ __forceinline__ uint64_t pooled_kth_key(const uint64_t* __restrict__ 
 // warp reductions pipeline instead of costing one full REDUX latency per step and query (measured before: 3.3 us per
 // query done one after the other, 26 us per warp and refresh; the lane-per-query variant of GPU call 6 was fine at
 // k = 10 but needed k / 4 registers per lane and spilled at k = 100).
-__device__ __forceinline__ void pooled_floor_batch8(const uint64_t* __restrict__ pool, int n_ctas, int ew, int nq,
-                                                    int k, int lane, uint64_t (&out)[8]) {
+// Returns a bit mask of the queries (bit j = query ew + 4 j) whose k-th pooled SCORE is shared by several keys: the
+// signature of a tie-heavy corpus, where the caller also consults the CTAs' own k-th keys (pooled_max_kth).
+__device__ __forceinline__ uint32_t pooled_floor_batch8(const uint64_t* __restrict__ pool, int n_ctas, int ew, int nq,
+                                                        int k, int lane, uint64_t (&out)[8]) {
+  uint32_t ties = 0u;
   constexpr int NC = kPoolMaxCtas / 32;
   uint32_t hi[8][NC], lo[8][NC];
 #pragma unroll
@@ -182,7 +186,7 @@ __device__ __forceinline__ void pooled_floor_batch8(const uint64_t* __restrict__
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const int c = lane + 32 * i;
-      const uint64_t x = (q < nq && c < n_ctas) ? __ldcg(pool + (size_t(c) * kPoolM) * kNQ + q) : 0ull;
+      const uint64_t x = (q < nq && c < n_ctas) ? __ldcg(pool + (size_t(c) * kPoolSlots) * kNQ + q) : 0ull;
       lo[j][i] = uint32_t(x);
       hi[j][i] = uint32_t(x >> 32);
     }
@@ -218,6 +222,7 @@ __device__ __forceinline__ void pooled_floor_batch8(const uint64_t* __restrict__
     }
     c_gt = __reduce_add_sync(0xffffffffu, c_gt);
     c_eq = __reduce_add_sync(0xffffffffu, c_eq);
+    if (c_eq > 1) ties |= 1u << j;      // warp-uniform (c_eq is a reduction result)
     const int need = k - c_gt;
     if (need >= c_eq) {
       out[j] = (uint64_t(t[j]) << 32) | __reduce_min_sync(0xffffffffu, lo_min);
@@ -234,6 +239,24 @@ __device__ __forceinline__ void pooled_floor_batch8(const uint64_t* __restrict__
       out[j] = (uint64_t(t[j]) << 32) | l;
     }
   }
+  return ties;
+}
+
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+  const uint32_t hi = __reduce_max_sync(0xffffffffu, uint32_t(v >> 32));
+  const uint32_t lo = __reduce_max_sync(0xffffffffu, (uint32_t(v >> 32) == hi) ? uint32_t(v) : 0u);
+  return (uint64_t(hi) << 32) | lo;
+}
+// max over the CTAs of their own k-th key for query q (the lanes split the CTAs)
+__device__ __forceinline__ uint64_t pooled_max_kth(const uint64_t* __restrict__ pool, int n_ctas, int q, int lane) {
+  uint64_t best = 0ull;
+#pragma unroll
+  for (int i = 0; i < kPoolMaxCtas / 32; ++i) {
+    const int c = lane + 32 * i;
+    const uint64_t x = c < n_ctas ? __ldcg(pool + (size_t(c) * kPoolSlots + kPoolM) * kNQ + q) : 0ull;
+    best = x > best ? x : best;
+  }
+  return warp_max_u64(best);
 }
 
 template <int KLIST, int CAP, int STAGES>
@@ -452,7 +475,14 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
     auto publish = [&](int q) {
       if (pool != nullptr && lane < kPoolM) {
         const uint64_t kk = keys[q * L::kKeysPerQuery + lane];
-        if (kk) pool[(size_t(blockIdx.x) * kPoolM + lane) * kNQ + q] = kk;
+        if (kk) pool[(size_t(blockIdx.x) * kPoolSlots + lane) * kNQ + q] = kk;
+      }
+      if (pool != nullptr && lane == kPoolM) {
+        // this CTA's own k-th key: it alone holds k rows at or above it, so the MAXIMUM of these over the CTAs is a
+        // floor too -- the tight one when scores tie massively (duplicate rows), where a CTA's best keys all sit in
+        // one tile and the pooled best keys trail far behind the true k-th key
+        const uint64_t kth = keys[q * L::kKeysPerQuery + k - 1];
+        if (kth) pool[(size_t(blockIdx.x) * kPoolSlots + kPoolM) * kNQ + q] = kth;
       }
     };
     // raise the thresholds to the pooled floor (all four select warps; see the comment at kPoolM)
@@ -478,18 +508,26 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_corpus, const __grid_c
           for (int w2 = 1; w2 < 4; ++w2) pf = part_floor[w2 * kNQ + q] < pf ? part_floor[w2 * kNQ + q] : pf;
           raise_to(q, pf);
         }
+        for (int q = ew; q < nq; q += 4) {           // and the largest own-k-th key of any CTA
+          const uint64_t mk = pooled_max_kth(pool, int(gridDim.x), q, lane);
+          if (lane == 0) raise_to(q, mk);
+        }
       } else if (5 * k <= 4 * int(gridDim.x)) {
         // k below the CTA count: the CTAs' best keys suffice; this warp's eight queries are bisected together
         uint64_t pf[8];
-        pooled_floor_batch8(pool, int(gridDim.x), ew, nq, k, lane, pf);
-        if (lane == 0) {
+        const uint32_t ties = pooled_floor_batch8(pool, int(gridDim.x), ew, nq, k, lane, pf);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) raise_to(ew + 4 * j, pf[j]);
+        for (int j = 0; j < 8; ++j) {
+          const int q = ew + 4 * j;
+          // the CTAs' own k-th keys are consulted only where scores tie (it costs 5 loads + 2 reductions per query)
+          const uint64_t mk = (q < nq && ((ties >> j) & 1u)) ? pooled_max_kth(pool, int(gridDim.x), q, lane) : 0ull;
+          if (lane == 0) raise_to(q, mk > pf[j] ? mk : pf[j]);
         }
       } else {
         for (int q = ew; q < nq; q += 4) {
           const uint64_t pf = pooled_kth_key(pool, int(gridDim.x), q, k, lane);
-          if (lane == 0) raise_to(q, pf);
+          const uint64_t mk = pooled_max_kth(pool, int(gridDim.x), q, lane);
+          if (lane == 0) raise_to(q, mk > pf ? mk : pf);
         }
       }
     };
@@ -1083,7 +1121,7 @@ SearchPlan plan_search(int k) {
   if (p.grid <= 0) p.grid = 148;
   p.keys_bytes = ((size_t(p.grid) * kNQ * k * 8) + 255) & ~size_t(255);
   p.minmax_bytes = ((size_t(p.grid) * kNQ * 2 * 4) + 255) & ~size_t(255);
-  p.pool_bytes = p.grid <= kPoolMaxCtas ? ((size_t(kNQ) * p.grid * kPoolM * 8 + 255) & ~size_t(255)) : 0;
+  p.pool_bytes = p.grid <= kPoolMaxCtas ? ((size_t(kNQ) * p.grid * kPoolSlots * 8 + 255) & ~size_t(255)) : 0;
   return p;
 }
 
