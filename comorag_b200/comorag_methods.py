@@ -175,7 +175,8 @@ class RetrievalWave:
             for i in range(n):
                 out[i]["timeline"] = (id(level_store), k,
                                       [level_store.texts[j] for j in ids[i] if j >= 0],
-                                      [float(s) for s, j in zip(norm[i], ids[i]) if j >= 0])
+                                      [float(s) for s, j in zip(norm[i], ids[i]) if j >= 0],
+                                      len(level_store.hash_ids))
         by_query = dict(zip(uniq, out))
         return [by_query[q] for q in queries]
 
@@ -242,7 +243,7 @@ def get_fact_scores(self, query: str) -> np.ndarray:
     wave = getattr(self, "_crag_wave", None)
     hit = wave.lookup(query) if wave is not None else None
     if hit is not None:
-        return hit["fact_scores"]
+        return hit["fact_scores"].copy()      # callers own the array, as with the reference's fresh np result
     query_embedding = _query_embedding(self, 'triple', query, _INSTRUCTION_FACT)
     return retrieval.get_fact_scores(self.fact_embeddings.index, query_embedding)
 

@@ -1,9 +1,9 @@
 """Retrieval math of ComoRAG.py / utils/embed_utils.py on the fused top-k kernel.
 
-Each function keeps the reference function's name, arguments and return convention; where the reference
-returns a FULL ranking of all N rows (dense_passage_retrieval feeds every rank into PPR,
-ComoRAG.py:1034-1042) an exact full-sort path is kept for small N and the top-k path is used for large N
-(the narrowing is documented in DESIGN.md).
+Each function keeps the reference function's name, arguments and return convention.  Where the reference returns a
+FULL ranking of all N rows (dense_passage_retrieval feeds every rank into PPR, ComoRAG.py:1034-1042) the scores come
+from one score-all pass of the search kernel and the permutation from the device radix sort, at any shard size; the
+truncated variants (top_k given) use the fused top-k kernel.  There is no host or library fallback.
 """
 from __future__ import annotations
 
@@ -79,7 +79,7 @@ _parked_lock = __import__("threading").Lock()
 
 def park_similar_summaries(query: str, result) -> None:
     """A retrieval wave (comorag_methods.RetrievalWave) already ran the timeline search for `query`; keep its
-    (store id, k, texts, scores) until get_similar_summaries asks for it."""
+    (store id, k, texts, scores, rows in the store at search time) until get_similar_summaries asks for it."""
     with _parked_lock:
         _parked_summaries[query] = result
         while len(_parked_summaries) > 512:
@@ -94,7 +94,8 @@ def get_similar_summaries(query: str, level_store, embedding_model, top_k: int =
         return [], []
     with _parked_lock:
         parked = _parked_summaries.get(query)
-    if parked is not None and parked[0] == id(level_store) and parked[1] >= min(top_k, len(level_ids)):
+    if (parked is not None and parked[0] == id(level_store) and parked[1] >= min(top_k, len(level_ids))
+            and parked[4] == len(level_ids)):      # rows added since the wave ran: search again
         k = min(top_k, len(level_ids))
         return list(parked[2][:k]), list(parked[3][:k])
     query_embedding = embedding_model.batch_encode(

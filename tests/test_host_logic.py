@@ -370,3 +370,10 @@ def test_retrieval_wave_shares_one_pass_per_shard_between_concurrent_tri_retriev
         raw = (e @ mats["level"].T)[0]
         want = np.argsort(-raw, kind="stable")[:3]
         assert epi[0] == [f"level text {i}" for i in want]
+    # a timeline row added after the wave ran: the parked result is stale and the search runs again
+    before = passes["level"]
+    mats["level"] = np.concatenate([mats["level"], rng.standard_normal((1, D)).astype(np.float32)])
+    stores["level"].hash_ids.append("level-4")
+    stores["level"].texts.append("level text 4")
+    rt.get_similar_summaries(queries[0], rag.level_store, rag.embedding_model, top_k=3)
+    assert passes["level"] == before + 1
