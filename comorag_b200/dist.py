@@ -1,6 +1,8 @@
 """Row-sharded index across the GPUs of one box: one process per GPU (torch.distributed), each rank scans
-its own shard with the fused kernel, ONE all-gather of the packed per-rank (ids, scores, min/max) and a
-merge kernel give every rank the global top-k.
+its own shard with the fused kernel; the per-rank (ids, scores, min/max) records then reach every rank either by
+the fused finalize + exchange + merge kernel over NVLink peer memory (PeerExchange, the default under NCCL) or by ONE
+all_gather_into_tensor of the packed records + a merge kernel (the formulation north_star names) -- either way every
+rank ends with the global top-k.
 
 Rank r owns global rows [offsets[r], offsets[r+1]); ids written by the shard kernel are already global.
 The reference has no distributed code -- this is the exchange step the shard layout adds.
@@ -188,7 +190,10 @@ class ShardedIndex:
         """Host-buffer entry point on every rank: numpy / torch queries [nq, dim] in, numpy (ids, scores, minmax) out."""
         q = self.local.prepare_queries(queries)
         ids, scores, mm = self.search_device(q, k)
-        return ids.cpu().numpy(), scores.cpu().numpy(), mm.cpu().numpy()
+        ids_h = ids.cpu().numpy()
+        if self.peer is not None and ids_h.size and (ids_h[:, 0] < 0).any():
+            self.peer.check()        # the exchange kernel answers an all-empty row when a peer's record never arrived
+        return ids_h, scores.cpu().numpy(), mm.cpu().numpy()
 
 
 def pair_bounds(n_pairs: int, world: int) -> List[int]:

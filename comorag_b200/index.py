@@ -178,23 +178,26 @@ class DenseIndex:
             v = v[None, :]
         if v.shape[1] != self.dim:
             raise ValueError(f"expected [n, {self.dim}] vectors, got {tuple(v.shape)}")
-        with self._lock:
-            n0, n1 = self._n, self._n + v.shape[0]
-            self._reserve(n1)
-            self._buf[n0:n1, : self.dim] = v.to(self.device, non_blocking=True).to(torch.bfloat16)
-            self._n = n1
+        with torch.cuda.device(self.device):
+            vb = v.to(self.device, non_blocking=True).to(torch.bfloat16)   # H2D + cast before the lock: searches keep running
+            with self._lock:
+                n0, n1 = self._n, self._n + vb.shape[0]
+                self._reserve(n1)
+                self._buf[n0:n1, : self.dim] = vb
+                self._n = n1
 
     def add_bf16_file(self, path: str, n_rows: int) -> None:
         """Append n_rows raw bf16 [*, dim_pad] rows from a file written by EmbeddingStore's append-only persistence."""
         raw = np.fromfile(path, dtype=np.int16, count=n_rows * self.dim_pad)
         if raw.size != n_rows * self.dim_pad:
             raise ValueError(f"{path}: expected {n_rows} rows of {self.dim_pad} bf16")
-        rows = torch.from_numpy(raw).view(torch.bfloat16).view(n_rows, self.dim_pad)
-        with self._lock:
-            n0, n1 = self._n, self._n + n_rows
-            self._reserve(n1)
-            self._buf[n0:n1] = rows.to(self.device, non_blocking=True)
-            self._n = n1
+        with torch.cuda.device(self.device):
+            rows = torch.from_numpy(raw).view(torch.bfloat16).view(n_rows, self.dim_pad).to(self.device, non_blocking=True)
+            with self._lock:
+                n0, n1 = self._n, self._n + n_rows
+                self._reserve(n1)
+                self._buf[n0:n1] = rows
+                self._n = n1
 
     def save(self, path: str) -> None:
         """Raw bf16 [n_rows, dim_pad] dump + json meta (per-rank shard file for a sharded index)."""
