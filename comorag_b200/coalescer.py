@@ -19,6 +19,10 @@ from typing import Any, Callable, Hashable, List, Optional, Sequence, Tuple
 import numpy as np
 
 
+class BatcherClosed(RuntimeError):
+    """submit() after close(): the caller should run its request directly."""
+
+
 class Batcher:
     """fn(group_key, [payload, ...]) -> [result, ...] (same length, same order)."""
 
@@ -27,25 +31,32 @@ class Batcher:
         self._fn, self._max_items, self._max_wait, self._weight = fn, max_items, max_wait_s, weight
         self._q: "queue.Queue[Tuple[Hashable, Any, Future]]" = queue.Queue()
         self._closed = False
+        self._gate = threading.Lock()   # closed-check + enqueue are one step: nothing can land behind the shutdown sentinel
         self.batches = 0   # statistics: number of fn calls / payloads served
         self.items = 0
         self._t = threading.Thread(target=self._run, name=name, daemon=True)
         self._t.start()
 
     def submit(self, key: Hashable, payload: Any) -> Future:
-        if self._closed:
-            raise RuntimeError("batcher is closed")
         f: Future = Future()
-        self._q.put((key, payload, f))
+        with self._gate:
+            if self._closed:
+                raise BatcherClosed("batcher is closed")
+            self._q.put((key, payload, f))
         return f
 
     def call(self, key: Hashable, payload: Any) -> Any:
         return self.submit(key, payload).result()
 
     def close(self) -> None:
-        self._closed = True
-        self._q.put(None)  # type: ignore[arg-type]
-        self._t.join(timeout=5)
+        """Requests already queued are still served; later submit() calls raise BatcherClosed."""
+        with self._gate:
+            if self._closed:
+                return
+            self._closed = True
+            self._q.put(None)  # type: ignore[arg-type]
+        if threading.current_thread() is not self._t:
+            self._t.join(timeout=5)
 
     def _run(self) -> None:
         carry = None

@@ -20,6 +20,7 @@ from typing import Dict, List, Tuple
 import numpy as np
 
 from . import retrieval
+from .coalescer import BatcherClosed
 
 logger = logging.getLogger(__name__)
 
@@ -63,10 +64,32 @@ def _store_has_shard(store) -> bool:
     return hasattr(store, "index") and hasattr(store, "search")
 
 
+_prepare_lock = __import__("threading").RLock()
+
+
 def prepare_retrieval_objects(self) -> None:
     """ComoRAG.py:876-907 with the four `np.array(store.get_embeddings(keys))` pulls replaced by views of the
     stores' device shards.  Key lists, graph index maps and `ready_to_retrieve` are set exactly as the reference does.
     The key lists are `store.get_all_ids()`, i.e. store row order, so row r of a shard is key r of its list."""
+    with _prepare_lock:
+        _prepare_locked(self)
+
+
+def _store_signature(self):
+    stores = [self.entity_embedding_store, self.ver_embedding_store, self.fact_embedding_store]
+    if self.global_config.need_cluster:
+        stores.append(self.sem_embedding_store)
+    return tuple((id(s), len(s.hash_ids)) for s in stores) + (self.graph.vcount() if hasattr(self.graph, "vcount") else len(self.graph.vs),)
+
+
+def _prepare_locked(self) -> None:
+    # Up to 16 meta_control_loop threads reach `if not self.ready_to_retrieve: self.prepare_retrieval_objects()`
+    # together (ComoRAG.py:436-441, :467-468).  In the reference the duplicate calls rebuild identical matrices; here
+    # a late duplicate would retire the retrieval wave under the threads already using it, so a call that finds the
+    # objects prepared for exactly these stores and row counts returns at once.
+    sig = _store_signature(self)
+    if getattr(self, "ready_to_retrieve", False) and getattr(self, "_crag_prepared_for", None) == sig:
+        return
     logger.info("Preparing for fast retrieval.")
     self.query_to_embedding: Dict = {'triple': {}, 'passage': {}}
 
@@ -98,6 +121,7 @@ def prepare_retrieval_objects(self) -> None:
     if old is not None:          # shards were rebuilt: parked results belong to the previous ones
         old.close()
         self._crag_wave = None
+    self._crag_prepared_for = sig
     self.ready_to_retrieve = True
 
 
@@ -134,7 +158,10 @@ class RetrievalWave:
             hit = self._results.get(query)
         if hit is not None:
             return hit
-        res = self._b.call("tri_retrieve", query)
+        try:
+            res = self._b.call("tri_retrieve", query)
+        except BatcherClosed:        # the wave was retired (shards rebuilt) between _wave() and here: answer alone
+            res = self._run("tri_retrieve", [query])[0]
         with self._lock:
             self._results[query] = res
             while len(self._results) > self._keep:

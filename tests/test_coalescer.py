@@ -67,3 +67,24 @@ def test_failure_reaches_every_waiter():
         with pytest.raises(ValueError):
             f.result(timeout=2)
     b.close()
+
+
+def test_close_serves_what_is_queued_and_refuses_the_rest():
+    from comorag_b200.coalescer import BatcherClosed
+    release = threading.Event()
+
+    def slow(key, payloads):
+        release.wait(2)
+        return [p * 2 for p in payloads]
+
+    b = Batcher(slow, max_items=1, max_wait_s=1e-3)
+    futs = [b.submit("k", i) for i in range(4)]          # the worker blocks in the first batch, three wait in the queue
+    closer = threading.Thread(target=b.close)
+    closer.start()
+    time.sleep(0.05)
+    with pytest.raises(BatcherClosed):                   # nothing can be enqueued behind the shutdown sentinel
+        b.submit("k", 99)
+    release.set()
+    assert [f.result(timeout=3) for f in futs] == [0, 2, 4, 6]
+    closer.join(timeout=6)
+    b.close()                                            # idempotent

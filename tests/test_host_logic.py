@@ -377,3 +377,50 @@ def test_retrieval_wave_shares_one_pass_per_shard_between_concurrent_tri_retriev
     stores["level"].texts.append("level text 4")
     rt.get_similar_summaries(queries[0], rag.level_store, rag.embedding_model, top_k=3)
     assert passes["level"] == before + 1
+
+
+def test_prepare_retrieval_objects_from_many_threads_keeps_the_wave_and_refreshes_on_growth():
+    """ComoRAG.py:467-468 is reached by up to 16 threads at once: duplicate calls must not retire the retrieval wave
+    the earlier threads are already using; a call after the stores grew must rebuild and retire it."""
+    import types
+    from concurrent.futures import ThreadPoolExecutor
+
+    from comorag_b200 import comorag_methods as cm
+
+    class Store:
+        def __init__(self, name, n):
+            self.hash_ids = [f"{name}-{i}" for i in range(n)]
+            self._dim = 8
+            self.uploads = 0
+
+        def get_all_ids(self):
+            return list(self.hash_ids)
+
+        @property
+        def index(self):
+            self.uploads += 1
+            return object()
+
+        def search(self, q, k):
+            raise AssertionError("not used here")
+
+    ent, chunk, fact = Store("entity", 5), Store("chunk", 3), Store("fact", 7)
+    graph = types.SimpleNamespace(vs=[{"name": n} for n in ent.hash_ids + chunk.hash_ids])
+    rag = types.SimpleNamespace(global_config=types.SimpleNamespace(need_cluster=False), graph=graph,
+                                entity_embedding_store=ent, ver_embedding_store=chunk, fact_embedding_store=fact,
+                                ready_to_retrieve=False)
+    cm.prepare_retrieval_objects(rag)
+    assert rag.ready_to_retrieve and rag.fact_node_keys == fact.hash_ids and rag.passage_node_idxs == [5, 6, 7]
+    assert rag.fact_embeddings.shape == (7, 8) and rag.entity_embeddings.shape == (5, 8)
+    closed = []
+    rag._crag_wave = types.SimpleNamespace(close=lambda: closed.append(1))
+    rag.query_to_embedding["triple"]["q"] = "cached"
+    with ThreadPoolExecutor(8) as ex:                    # the late duplicates of the first tri_retrieve wave
+        list(ex.map(lambda _: cm.prepare_retrieval_objects(rag), range(16)))
+    assert not closed and rag._crag_wave is not None and rag.query_to_embedding["triple"] == {"q": "cached"}
+    fact.hash_ids.append("fact-7")                       # index() added rows: the next call rebuilds
+    cm.prepare_retrieval_objects(rag)
+    assert closed == [1] and rag._crag_wave is None and len(rag.fact_node_keys) == 8 and rag.query_to_embedding["triple"] == {}
+    with pytest.raises(TypeError):                       # a reference store (no device shard) is refused, not papered over
+        rag.fact_embedding_store = types.SimpleNamespace(hash_ids=[], get_all_ids=lambda: [])
+        cm.prepare_retrieval_objects(rag)
