@@ -83,5 +83,24 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+EXAMPLES = PKG_DIR.parent / "examples"
+EXAMPLE_BIN = EXAMPLES / "bin" / "c_host_search"
+
+
+def build_examples(force: bool = False) -> Path:
+    """examples/c_host_search.cu -> examples/bin/c_host_search: a host with no torch / Python in it, linked against the
+    C ABI only (rpath relative to the binary, so it runs wherever the repo snapshot lands)."""
+    src = EXAMPLES / "c_host_search.cu"
+    deps = [src, LIB_PATH, *INCLUDE.glob("*.h")]
+    if not force and EXAMPLE_BIN.exists() and all(p.stat().st_mtime <= EXAMPLE_BIN.stat().st_mtime for p in deps):
+        return EXAMPLE_BIN
+    EXAMPLE_BIN.parent.mkdir(parents=True, exist_ok=True)
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-lineinfo", "-I", str(INCLUDE),
+           str(src), "-o", str(EXAMPLE_BIN), "-L", str(LIB_DIR), "-lcomorag_b200",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../comorag_b200/lib"]
+    subprocess.run(cmd, check=True)
+    return EXAMPLE_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
