@@ -57,6 +57,19 @@ def parse_args():
     return ap.parse_args()
 
 
+def workload_config(rows: int, dim: int, nq: int, k: int, world: int) -> dict:
+    """The `config` object of BOTH arms' JSON lines: what is computed, nothing about how.  It depends on the command
+    line and the GPU count only, so `bench.py` and `bench.py --impl reference` print the same object for the same
+    flags (the driver compares them); what each arm's step consists of is said under `implementation` (ours) and
+    `sample` (the reference arm's bounded sample of the step)."""
+    base, rem = divmod(int(rows), int(world))        # comorag_b200.dist.shard_bounds: rank 0 owns base + (1 if rem) rows
+    rows_rank0 = base + (1 if rem else 0)
+    return {"workload": f"{rows}x{dim} bf16 index, brute-force IP top-{k}, {nq} probe queries per step, "
+                        f"row-sharded over {world} GPU(s)",
+            "index_rows": rows, "rows_per_rank": rows_rank0, "dim": dim, "queries_per_step": nq, "k": k,
+            "l2": f"inputs larger than L2 ({rows_rank0 * dim * 2 / 1e9:.2f} GB shard per rank vs 126 MB)"}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -372,9 +385,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 1), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.rows}x{args.dim} IP top-{args.k}, reference CPU path (per-query np.dot + min-max + full argsort "
-                                   f"over all {args.rows} rows); a step = 1 query, a bounded sample of the {args.nq}-query step",
-                       "index_rows": args.rows, "dim": args.dim, "queries_per_step": 1, "queries_per_full_step": args.nq, "k": args.k},
+            "config": workload_config(args.rows, args.dim, args.nq, args.k, max(int(args.gpus), 1)),
+            "sample": f"the reference's CPU path (ComoRAG.dense_passage_retrieval: per-query np.dot + min-max + full argsort over all "
+                      f"{args.rows} fp32 rows, host memory, no sharding); a timed step = 1 query, a bounded sample of the "
+                      f"{args.nq}-query step (the reference scores one query at a time anyway); value = queries/s, not extrapolated",
+            "queries_per_timed_step": 1,
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t_all}
@@ -636,12 +651,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.rows}x{args.dim} bf16 index, brute-force IP top-{args.k}, {args.nq} probe queries per step, "
-                                   f"row-sharded over {world} GPU(s)" + (f", exchange: {index.exchange_mode}" if world > 1 else ""),
-                       "index_rows": args.rows, "rows_per_rank": my_rows, "dim": args.dim, "queries_per_step": args.nq, "k": args.k,
-                       "step": ("one CUDA graph: " if use_graph else "") + " + ".join(kernels),
-                       "exchange": index.exchange_mode,
-                       "l2": f"inputs larger than L2 ({algo_bytes / 1e9:.2f} GB shard per rank vs 126 MB)"},
+            "config": workload_config(args.rows, args.dim, args.nq, args.k, world),
+            "implementation": {"step": ("one CUDA graph: " if use_graph else "") + " + ".join(kernels),
+                               "exchange": index.exchange_mode},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": args.steps * ours_per_step,
             "parity": parity,

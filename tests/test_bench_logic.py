@@ -56,3 +56,19 @@ def test_synthetic_vocab_and_texts_tokenise_one_token_per_word():
     assert len(vocab) == 1000 and vocab[:5] == ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"]
     texts = bench.synthetic_texts(3, 20, seed=1, vocab_size=1000)
     assert all(len(t.split()) == 20 and all(w in set(vocab) for w in t.split()) for t in texts)
+
+
+def test_both_arms_print_the_same_config_object():
+    """`bench.py` and `bench.py --impl reference` must describe the SAME workload (the driver compares the two
+    `config` objects); rank 0's row count is the one comorag_b200.dist.shard_bounds gives."""
+    import bench
+    from comorag_b200.dist import shard_bounds
+    for rows, world in ((10_000_000, 1), (10_000_000, 8), (1_000_003, 4)):
+        cfg = bench.workload_config(rows, 1024, 32, 10, world)
+        offs = shard_bounds(rows, world)
+        assert cfg["rows_per_rank"] == offs[1] - offs[0]
+        assert cfg["index_rows"] == rows and cfg["queries_per_step"] == 32 and cfg["k"] == 10
+        assert f"over {world} GPU(s)" in cfg["workload"] and "L2" in cfg["l2"]
+        assert cfg == bench.workload_config(rows, 1024, 32, 10, world)
+    src = open(bench.__file__).read()
+    assert src.count('"config": workload_config(') == 2      # our arm and the reference arm, nothing hand-written beside it
