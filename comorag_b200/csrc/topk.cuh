@@ -135,4 +135,42 @@ __device__ __forceinline__ void insert_few(uint64_t* qkeys, int c, int k, uint64
   __syncwarp();
 }
 
+// One warp streams `total` candidate keys (fetch(i), 0 = absent) through a KLIST+CAP selector (CAP >= 32).
+template <int KLIST, int CAP, class Fetch>
+__device__ __forceinline__ void select_stream(uint64_t* keys, uint64_t* thr_slot, int lane, int k, int total,
+                                              uint64_t bound, Fetch fetch) {
+  static_assert(CAP >= 32, "a batch of 32 candidates must fit the buffer");
+  for (int i = lane; i < KLIST + CAP; i += 32) keys[i] = 0ull;
+  if (lane == 0) *thr_slot = 0ull;
+  __syncwarp();
+  int c = 0;
+  constexpr int U = 4;  // batches fetched ahead: the lists sit in L2 / HBM, so 4 loads per lane are kept in flight
+  for (int base0 = 0; base0 < total; base0 += 32 * U) {
+    uint64_t pre[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base0 + u * 32 + lane;
+      pre[u] = idx < total ? fetch(idx) : 0ull;   // past-the-end batches are all zero and admit nothing
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t key = pre[u];
+      const uint64_t thr = *thr_slot > bound ? *thr_slot : bound;
+      const bool take = key != 0 && key >= thr;
+      const uint32_t m = __ballot_sync(0xffffffffu, take);
+      if (m != 0u) {
+        if (take) keys[KLIST + c + __popc(m & ((1u << lane) - 1u))] = key;
+        c += __popc(m);
+        __syncwarp();
+        if (c + 32 > CAP) {
+          flush_query<KLIST, CAP>(keys, c, k, thr_slot, lane);
+          c = 0;
+        }
+      }
+    }
+  }
+  if (c > 0) flush_query<KLIST, CAP>(keys, c, k, thr_slot, lane);
+  __syncwarp();
+}
+
 }  // namespace crag

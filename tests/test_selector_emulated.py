@@ -30,7 +30,7 @@ def test_selector_primitives_match_their_models_on_emulated_lanes(emu_binary):
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip().endswith("ALL OK")
     for group in ("warp_sort_desc<8>", "flush_query<128, 128>", "first-tile flush_query<128, 0>", "insert_few<128, 128>",
-                  "lane_kth_of_pool<4>", "pooled_floor_batch8", "pooled_kth_key / pooled_max_kth"):
+                  "select_stream<128, 128>", "lane_kth_of_pool<4>", "pooled_floor_batch8", "pooled_kth_key / pooled_max_kth"):
         assert f"ok  {group}" in r.stdout, group
 
 

@@ -4,6 +4,7 @@
 //   1. warp_sort_desc<EPL>      sorts 32*EPL keys descending (blocked layout), duplicates and zeros included
 //   2. flush_query<KLIST, CAP>  list u first c buffered candidates -> best k, descending, zero padded; thr = k-th key
 //   3. insert_few<KLIST, CAP>   the same contract for c <= kInsertMax candidates
+//   3b. select_stream<KLIST, CAP> sorted partial lists (per CTA / per rank) streamed through one selector -> global best k
 //   4. pooled floors            lane_kth_of_pool / pooled_floor_batch8 / pooled_kth_key / pooled_max_kth: the floor a
 //                               refresh derives from the published keys is reached by >= k distinct published keys
 //                               (the exactness invariant of the admission floor), and the bisection variants return
@@ -156,6 +157,41 @@ static void test_insert_few(int rounds) {
   printf("ok  insert_few<%d, %d>: %d random (k, list, <= %d candidates)\n", KLIST, CAP, rounds, kInsertMax);
 }
 
+// ------------------------------------------------------------------------------------------------ select_stream
+// the core of merge_topk_kernel / finalize_exchange_kernel: `parts` sorted lists of k keys each (the per-CTA or per-rank
+// partial results, zero padded when a part holds fewer) streamed through one selector, pre-filtered by the largest k-th
+// key of any part
+template <int KLIST, int CAP>
+static void test_select_stream(int rounds) {
+  for (int r = 0; r < rounds; ++r) {
+    const int k = 1 + int(rng() % KLIST);
+    const int parts = 1 + int(rng() % 40);
+    const int levels = (r % 3 == 0) ? 3 : 0;
+    std::vector<uint64_t> pool = distinct_keys(parts * k, levels);
+    std::vector<uint64_t> lists(size_t(parts) * k, 0ull), all;
+    uint64_t bound = 0;
+    for (int p = 0; p < parts; ++p) {
+      const int have = (rng() % 4 == 0) ? int(rng() % (k + 1)) : k;        // some parts saw fewer than k rows
+      std::vector<uint64_t> mine(pool.begin() + size_t(p) * k, pool.begin() + size_t(p) * k + have);
+      std::sort(mine.begin(), mine.end(), std::greater<uint64_t>());
+      for (int j = 0; j < have; ++j) { lists[size_t(p) * k + j] = mine[j]; all.push_back(mine[j]); }
+      if (have == k) bound = std::max(bound, mine[k - 1]);
+    }
+    if (r % 5 == 4) bound = 0;                                             // PAIRS mode streams without a bound
+    std::sort(all.begin(), all.end(), std::greater<uint64_t>());
+    std::vector<uint64_t> keys(KLIST + CAP, ~0ull);
+    uint64_t thr = ~0ull;
+    warp_emu::run_warp([&](int lane) {
+      select_stream<KLIST, CAP>(keys.data(), &thr, lane, k, parts * k, bound, [&](int idx) -> uint64_t { return lists[idx]; });
+    });
+    for (int j = 0; j < KLIST; ++j) {
+      const uint64_t w = (j < k && j < int(all.size())) ? all[j] : 0ull;
+      REQUIRE(keys[j] == w, "select_stream<%d,%d> k=%d parts=%d rank %d", KLIST, CAP, k, parts, j);
+    }
+  }
+  printf("ok  select_stream<%d, %d>: %d random sets of sorted partial lists\n", KLIST, CAP, rounds);
+}
+
 // ---------------------------------------------------------------------------------------------- 4. pooled floors
 struct Pool {
   int n_ctas;
@@ -288,6 +324,9 @@ int main(int argc, char** argv) {
   test_direct_first<128>(30 * scale);
   test_insert_few<64, 64>(60 * scale);
   test_insert_few<128, 128>(60 * scale);
+  test_select_stream<32, 32>(40 * scale);
+  test_select_stream<64, 64>(40 * scale);
+  test_select_stream<128, 128>(40 * scale);
   test_small_k_floor(12 * scale);
   test_batch8_floor(12 * scale);
   test_all_keys_floor(40 * scale);
