@@ -124,11 +124,22 @@ __device__ __forceinline__ uint64_t pooled_kth_key(const uint64_t* __restrict__ 
 #pragma unroll
   for (int i = 0; i < kPoolMaxCtas / 32; ++i) {
     const int c = lane + 32 * i;
+    uint64_t x[kPoolM];
+#pragma unroll
+    for (int m = 0; m < kPoolM; ++m) x[m] = c < n_ctas ? __ldcg(pool + (size_t(c) * kPoolSlots + m) * kNQ + q) : 0ull;
+    // The four slots of a CTA are four separate 8-byte stores: a publish that lands between two of these loads can
+    // show ONE row in two slots (when a better row arrives the CTA's keys move down a slot).  The floor must be the
+    // k-th largest over DISTINCT rows, so a key already seen in an earlier slot of the same CTA is dropped (keys are
+    // unique per row; entries of different CTAs are different rows by construction).
+#pragma unroll
+    for (int m = 1; m < kPoolM; ++m)
+#pragma unroll
+      for (int p = 0; p < m; ++p)
+        if (x[m] == x[p]) x[m] = 0ull;
 #pragma unroll
     for (int m = 0; m < kPoolM; ++m) {
-      const uint64_t x = c < n_ctas ? __ldcg(pool + (size_t(c) * kPoolSlots + m) * kNQ + q) : 0ull;
-      lo[kPoolM * i + m] = uint32_t(x);
-      hi[kPoolM * i + m] = uint32_t(x >> 32);
+      lo[kPoolM * i + m] = uint32_t(x[m]);
+      hi[kPoolM * i + m] = uint32_t(x[m] >> 32);
     }
   }
   return kth_largest_key<NV>(hi, lo, k);

@@ -219,13 +219,23 @@ static Pool make_pool(int n_ctas, int levels, double p_empty) {
   return p;
 }
 
+// the DISTINCT rows the pool vouches for (a torn read can show one row of a CTA in two of its slots)
 static std::vector<uint64_t> published(Pool& p, int q, int slots) {
   std::vector<uint64_t> v;
   for (int c = 0; c < p.n_ctas; ++c)
     for (int m = 0; m < slots; ++m)
       if (p.at(c, m, q)) v.push_back(p.at(c, m, q));
   std::sort(v.begin(), v.end(), std::greater<uint64_t>());
+  v.erase(std::unique(v.begin(), v.end()), v.end());
   return v;
+}
+// what a reader can see when a CTA publishes between its loads of slot m and slot m + 1: the old key of slot m, then
+// the new key of slot m + 1 -- which is that same row, moved down by the better row that arrived
+static void tear_some_entries(Pool& p, int q, int how_many) {
+  for (int t = 0; t < how_many; ++t) {
+    const int c = int(rng() % p.n_ctas), m = int(rng() % (kPoolM - 1));
+    if (p.at(c, m, q)) p.at(c, m + 1, q) = p.at(c, m, q);
+  }
 }
 static int count_ge(const std::vector<uint64_t>& v, uint64_t f) {
   return int(std::count_if(v.begin(), v.end(), [&](uint64_t x) { return x >= f; }));
@@ -296,6 +306,7 @@ static void test_all_keys_floor(int rounds) {
     const int levels = (r % 2 == 0) ? 2 + int(rng() % 3) : 0;
     Pool p = make_pool(n_ctas, levels, (r % 5 == 0) ? 0.3 : 0.0);
     const int q = int(rng() % kNQ);
+    if (r % 2) tear_some_entries(p, q, 1 + int(rng() % 24));
     uint64_t got = 1, got_max = 1;
     warp_emu::run_warp([&](int lane) {
       const uint64_t f = pooled_kth_key(p.t.data(), n_ctas, q, k, lane);
