@@ -1,8 +1,14 @@
-// 32 emulated lanes of one warp on the CPU: each lane is a ucontext fiber, a warp-collective (shuffle, reduction,
-// ballot, __syncwarp) is a barrier at which the fibers hand values over through a slot array.  Lanes run one at a time
-// and only switch at collectives, so plain shared arrays behave like shared memory between __syncwarp()s.  Every lane
-// must reach every collective (as on the GPU with a full mask); a lane that exits while others wait is reported as a
-// deadlock instead of hanging the test.
+// CUDA thread blocks on the CPU, for the pure-SIMT parts of the search kernels.  Every CUDA thread of one block is a
+// ucontext fiber; fibers run one at a time and switch only at synchronisation points, so plain arrays behave like
+// shared memory between barriers:
+//   * a warp collective (shuffle, ballot, reduction, match, __syncwarp) is a barrier of the 32 lanes of one warp at
+//     which values are handed over through a slot array;
+//   * __syncthreads() is a barrier of the block's live threads (threads that returned no longer count, as on the GPU);
+//   * a kernel "launch" runs its blocks one after the other (blockIdx 0, 1, ...).
+// All state is thread_local: a test that needs several blocks to make progress TOGETHER (the cross-rank exchange
+// kernel: block q of every rank waits for block q of every other rank) runs one OS thread per rank, each with its own
+// emulator, and real atomics between them (stub/cuda_runtime.h).  A collective that can never complete -- lanes
+// waiting for a lane that already returned -- is reported as a deadlock instead of hanging the test.
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
@@ -11,128 +17,205 @@
 #include <ucontext.h>
 
 #include <functional>
+#include <vector>
 
 namespace warp_emu {
 
 constexpr int kLanes = 32;
 constexpr size_t kStackBytes = 512 << 10;
 
-struct Warp {
-  ucontext_t main, ctx[kLanes];
-  char* stacks[kLanes];
-  bool done[kLanes];
-  int cur = 0;
-  int arrived = 0;
-  uint64_t gen = 0;
-  uint64_t slot[kLanes];
-  std::function<void(int)> body;
+struct Fiber {
+  ucontext_t ctx;
+  char* stack = nullptr;
+  bool done = false;
 };
 
-inline Warp*& current() {
-  static Warp* w = nullptr;
-  return w;
-}
-inline int lane() { return current()->cur; }
+struct WarpState {
+  int live = 0, arrived = 0;
+  uint64_t gen = 0;
+  uint64_t slot[kLanes];
+};
 
-inline void yield_lane() {
-  Warp* w = current();
-  swapcontext(&w->ctx[w->cur], &w->main);
+struct Block {
+  ucontext_t main;
+  std::vector<Fiber> fibers;
+  std::vector<WarpState> warps;
+  int n_threads = 0, live = 0;
+  int bar_arrived = 0;
+  uint64_t bar_gen = 0;
+  uint64_t progress = 0;        // bumps whenever any barrier releases or a thread exits (deadlock detection)
+  int cur = 0;
+  unsigned block_idx = 0, grid_dim = 1;
+  std::function<void()> body;
+};
+
+// bumped by the __nanosleep stand-in: a thread that sleeps is waiting for memory ANOTHER OS thread will write
+inline uint64_t& spin_count() {
+  static thread_local uint64_t n = 0;
+  return n;
 }
 
-inline void barrier() {
-  Warp* w = current();
-  const uint64_t my = w->gen;
-  if (++w->arrived == kLanes) {
-    w->arrived = 0;
-    ++w->gen;
+inline Block*& current() {
+  static thread_local Block* b = nullptr;
+  return b;
+}
+
+struct Dim3 { unsigned x, y, z; };
+inline Dim3 thread_idx() { return Dim3{unsigned(current()->cur), 0u, 0u}; }
+inline Dim3 block_idx() { return Dim3{current()->block_idx, 0u, 0u}; }
+inline Dim3 block_dim() { return Dim3{unsigned(current()->n_threads), 1u, 1u}; }
+inline Dim3 grid_dim() { return Dim3{current()->grid_dim, 1u, 1u}; }
+inline int lane() { return current()->cur & (kLanes - 1); }
+
+inline void yield_thread() {
+  Block* b = current();
+  swapcontext(&b->fibers[b->cur].ctx, &b->main);
+}
+
+inline void barrier() {            // the 32 lanes of the calling thread's warp
+  Block* b = current();
+  WarpState& w = b->warps[b->cur / kLanes];
+  const uint64_t my = w.gen;
+  if (++w.arrived >= w.live) {
+    w.arrived = 0;
+    ++w.gen;
+    ++b->progress;
   }
-  while (w->gen == my) yield_lane();
+  while (w.gen == my) yield_thread();
+}
+
+inline void sync_block() {         // __syncthreads()
+  Block* b = current();
+  const uint64_t my = b->bar_gen;
+  if (++b->bar_arrived >= b->live) {
+    b->bar_arrived = 0;
+    ++b->bar_gen;
+    ++b->progress;
+  }
+  while (b->bar_gen == my) yield_thread();
 }
 
 // every lane deposits v; lane l receives the value of lane src_of(l)
 template <class T, class F>
 inline T exchange(T v, F src_of) {
   static_assert(sizeof(T) <= 8, "exchange moves at most 64 bits");
-  Warp* w = current();
-  const int me = w->cur;
+  Block* b = current();
+  WarpState& w = b->warps[b->cur / kLanes];
+  const int me = b->cur & (kLanes - 1);
   uint64_t bits = 0;
   memcpy(&bits, &v, sizeof(T));
-  w->slot[me] = bits;
+  w.slot[me] = bits;
   barrier();
-  const uint64_t got = w->slot[src_of(me) & (kLanes - 1)];
+  const uint64_t got = w.slot[src_of(me) & (kLanes - 1)];
   barrier();                       // nobody overwrites a slot before every lane has read
   T r;
   memcpy(&r, &got, sizeof(T));
   return r;
 }
 
+// every lane receives f(all 32 deposited values)
 template <class T, class F>
-inline T reduce(T v, F op) {
-  Warp* w = current();
+inline auto gather(T v, F f) -> decltype(f(static_cast<const T*>(nullptr))) {
+  static_assert(sizeof(T) <= 8, "gather moves at most 64 bits");
+  Block* b = current();
+  WarpState& w = b->warps[b->cur / kLanes];
   uint64_t bits = 0;
   memcpy(&bits, &v, sizeof(T));
-  w->slot[w->cur] = bits;
+  w.slot[b->cur & (kLanes - 1)] = bits;
   barrier();
-  T acc;
-  memcpy(&acc, &w->slot[0], sizeof(T));
-  for (int l = 1; l < kLanes; ++l) {
-    T x;
-    memcpy(&x, &w->slot[l], sizeof(T));
-    acc = op(acc, x);
-  }
+  T all[kLanes];
+  for (int l = 0; l < kLanes; ++l) memcpy(&all[l], &w.slot[l], sizeof(T));
+  auto r = f(static_cast<const T*>(all));
   barrier();
-  return acc;
+  return r;
+}
+
+template <class T, class F>
+inline T reduce(T v, F op) {
+  return gather(v, [&](const T* all) {
+    T acc = all[0];
+    for (int l = 1; l < kLanes; ++l) acc = op(acc, all[l]);
+    return acc;
+  });
 }
 
 inline void trampoline() {
-  Warp* w = current();
-  w->body(w->cur);
-  w->done[w->cur] = true;
+  Block* b = current();
+  b->body();
+  Fiber& f = b->fibers[b->cur];
+  f.done = true;
+  // a thread that returns stops counting towards the barriers it might have been expected at
+  --b->live;
+  WarpState& w = b->warps[b->cur / kLanes];
+  --w.live;
+  ++b->progress;
+  if (w.arrived > 0 && w.arrived >= w.live) { w.arrived = 0; ++w.gen; }
+  if (b->bar_arrived > 0 && b->bar_arrived >= b->live) { b->bar_arrived = 0; ++b->bar_gen; }
 }
 
-// run body(lane) on 32 lanes to completion
-inline void run_warp(const std::function<void(int)>& body) {
-  Warp* w = new Warp;
-  Warp* outer = current();
-  current() = w;
-  w->body = body;
-  for (int l = 0; l < kLanes; ++l) {
-    w->done[l] = false;
-    w->stacks[l] = static_cast<char*>(malloc(kStackBytes));
-    getcontext(&w->ctx[l]);
-    w->ctx[l].uc_stack.ss_sp = w->stacks[l];
-    w->ctx[l].uc_stack.ss_size = kStackBytes;
-    w->ctx[l].uc_link = &w->main;
-    makecontext(&w->ctx[l], reinterpret_cast<void (*)()>(trampoline), 0);
+// one thread block of n_threads CUDA threads (a multiple of 32), all running body() to completion
+inline void run_block(int n_threads, unsigned block_index, unsigned grid, const std::function<void()>& body) {
+  if (n_threads % kLanes != 0) { fprintf(stderr, "warp_emu: block size must be a multiple of 32\n"); abort(); }
+  Block* b = new Block;
+  Block* outer = current();
+  current() = b;
+  b->body = body;
+  b->n_threads = b->live = n_threads;
+  b->block_idx = block_index;
+  b->grid_dim = grid;
+  b->fibers.resize(n_threads);
+  b->warps.resize(n_threads / kLanes);
+  for (auto& w : b->warps) w.live = kLanes;
+  for (int t = 0; t < n_threads; ++t) {
+    Fiber& f = b->fibers[t];
+    f.stack = static_cast<char*>(malloc(kStackBytes));
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = kStackBytes;
+    f.ctx.uc_link = &b->main;
+    makecontext(&f.ctx, reinterpret_cast<void (*)()>(trampoline), 0);
   }
   int stuck_sweeps = 0;
-  while (true) {
-    int alive = 0, finished_before = 0;
-    for (int l = 0; l < kLanes; ++l) finished_before += w->done[l];
-    const uint64_t gen_before = w->gen;
-    const int arrived_before = w->arrived;
-    for (int l = 0; l < kLanes; ++l) {
-      if (w->done[l]) continue;
-      ++alive;
-      w->cur = l;
-      swapcontext(&w->main, &w->ctx[l]);
+  uint64_t spinning_sweeps = 0;
+  while (b->live > 0) {
+    const uint64_t before = b->progress;
+    const uint64_t spins_before = spin_count();
+    const int arrived_before = b->bar_arrived;
+    int warp_arrived_before = 0;
+    for (auto& w : b->warps) warp_arrived_before += w.arrived;
+    for (int t = 0; t < n_threads; ++t) {
+      if (b->fibers[t].done) continue;
+      b->cur = t;
+      swapcontext(&b->main, &b->fibers[t].ctx);
     }
-    if (alive == 0) break;
-    int finished_after = 0;
-    for (int l = 0; l < kLanes; ++l) finished_after += w->done[l];
-    if (w->gen == gen_before && w->arrived == arrived_before && finished_after == finished_before) {
-      if (++stuck_sweeps > 4) {
-        fprintf(stderr, "warp_emu: deadlock -- %d lanes wait at a collective that %d finished lanes never reach\n",
-                w->arrived, finished_after);
+    int warp_arrived_after = 0;
+    for (auto& w : b->warps) warp_arrived_after += w.arrived;
+    if (b->progress == before && b->bar_arrived == arrived_before && warp_arrived_after == warp_arrived_before && b->live > 0) {
+      // nothing moved in a whole sweep.  Threads sleeping in a spin-wait on memory another OS thread will write (the
+      // exchange kernel's flag wait) are legitimate and get a long leash; anything else is a lost collective.
+      const bool spinning = spin_count() != spins_before;
+      if (spinning ? ++spinning_sweeps > (uint64_t(1) << 24) : ++stuck_sweeps > 4) {
+        fprintf(stderr, "warp_emu: deadlock in block %u -- %d live threads, %d at __syncthreads, %d at warp collectives\n",
+                block_index, b->live, b->bar_arrived, warp_arrived_after);
         abort();
       }
     } else {
       stuck_sweeps = 0;
     }
   }
-  for (int l = 0; l < kLanes; ++l) free(w->stacks[l]);
-  delete w;
+  for (auto& f : b->fibers) free(f.stack);
+  delete b;
   current() = outer;
+}
+
+// kernel<<<grid, block>>>: blocks run one after the other
+inline void launch(unsigned grid, int block, const std::function<void()>& kernel_call) {
+  for (unsigned bidx = 0; bidx < grid; ++bidx) run_block(block, bidx, grid, kernel_call);
+}
+
+// one warp, body(lane): what the selector-primitive tests use
+inline void run_warp(const std::function<void(int)>& body) {
+  run_block(kLanes, 0, 1, [&]() { body(lane()); });
 }
 
 }  // namespace warp_emu
