@@ -1,0 +1,114 @@
+"""The SIMT parts of the search kernels on the CPU.  csrc/topk.cuh, pool_floor.cuh, merge_kernels.cuh and
+rank_kernels.cuh hold no tcgen05 / TMA / mbarrier code, so the SAME headers the library compiles are compiled for the
+host with CUDA threads as fibers (tests/warp_emu: warp collectives, __syncthreads, shared memory, one OS thread per
+rank with real atomics for the cross-rank exchange) and checked against plain C++ models:
+  selector_emu_test.cpp  bitonic sort, flush / insert list maintenance, select_stream, and the pooled admission
+                         floors -- above all the property exactness rests on: >= k published keys reach the floor
+  kernel_emu_test.cpp    the radix-rank kernels (full permutation == stable descending sort), merge_topk_kernel in
+                         both layouts, and finalize_exchange_kernel on 2 / 3 / 4 / 8 ranks, calls back to back with
+                         a deliberately slow reader (the slot-parity protocol)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "warp_emu")
+CSRC = os.path.join(ROOT, "comorag_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu_binary(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not installed")
+    exe = tmp_path_factory.mktemp("warp_emu") / "selector_emu_test"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wno-unknown-pragmas", "-pthread", "-I", os.path.join(EMU, "stub"), "-I", CSRC,
+                        os.path.join(EMU, "selector_emu_test.cpp"), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def _build_kernel_test(csrc_dir, exe):
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wno-unknown-pragmas", "-pthread", "-I", os.path.join(EMU, "stub"), "-I", str(csrc_dir),
+                        os.path.join(EMU, "kernel_emu_test.cpp"), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+@pytest.fixture(scope="module")
+def kernel_binary(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not installed")
+    return _build_kernel_test(CSRC, tmp_path_factory.mktemp("warp_emu_k") / "kernel_emu_test")
+
+
+def test_selector_primitives_match_their_models_on_emulated_lanes(emu_binary):
+    r = subprocess.run([str(emu_binary), "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("ALL OK")
+    for group in ("warp_sort_desc<8>", "flush_query<128, 128>", "first-tile flush_query<128, 0>", "insert_few<128, 128>",
+                  "select_stream<128, 128>", "lane_kth_of_pool<4>", "pooled_floor_batch8", "pooled_kth_key / pooled_max_kth"):
+        assert f"ok  {group}" in r.stdout, group
+
+
+def test_the_emulated_headers_are_the_ones_the_kernel_includes():
+    """No copy of the selector lives under tests/: the emulation includes csrc/topk.cuh and csrc/pool_floor.cuh, and
+    search.cu includes the same two files."""
+    test_src = open(os.path.join(EMU, "selector_emu_test.cpp")).read()
+    assert '#include "topk.cuh"' in test_src and '#include "pool_floor.cuh"' in test_src
+    kernel_src = open(os.path.join(CSRC, "search.cu")).read()
+    assert '#include "topk.cuh"' in kernel_src and '#include "pool_floor.cuh"' in kernel_src
+    ktest_src = open(os.path.join(EMU, "kernel_emu_test.cpp")).read()
+    assert '#include "merge_kernels.cuh"' in ktest_src and '#include "rank_kernels.cuh"' in ktest_src
+    assert '#include "merge_kernels.cuh"' in kernel_src
+    assert '#include "rank_kernels.cuh"' in open(os.path.join(CSRC, "rank_all.cu")).read()
+    for name in os.listdir(EMU):
+        assert not name.endswith(".cuh"), f"{name}: kernel headers must not be duplicated under tests/"
+
+
+def test_emulation_catches_a_broken_floor(emu_binary, tmp_path):
+    """Mutation check: a floor bisection that counts `>` instead of `>=` (a floor one key too high -- it would drop a
+    true top-k row) must fail the property test."""
+    mutated = tmp_path / "csrc"
+    mutated.mkdir()
+    for h in ("topk.cuh", "pool_floor.cuh"):
+        shutil.copy(os.path.join(CSRC, h), mutated / h)
+    src = (mutated / "pool_floor.cuh").read_text()
+    needle = "for (int i = 0; i < NC; ++i) c += (hi[j][i] >= cand) ? 1 : 0;"
+    assert src.count(needle) == 1
+    (mutated / "pool_floor.cuh").write_text(src.replace(needle, needle.replace(">= cand", "> cand")))
+    exe = tmp_path / "mutant"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wno-unknown-pragmas", "-I", os.path.join(EMU, "stub"), "-I", str(mutated),
+                        os.path.join(EMU, "selector_emu_test.cpp"), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "FAILED" in r.stderr
+
+
+def test_rank_merge_and_exchange_kernels_on_emulated_blocks(kernel_binary):
+    r = subprocess.run([str(kernel_binary), "1"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("ALL OK")
+    for group in ("rank kernels: n = 6000", "merge_topk_kernel<128, 128, keys>", "merge_topk_kernel<64, 64, packed records>",
+                  "finalize_exchange_kernel<64, 64>: world = 3", "finalize_exchange_kernel<128, 128>: world = 8"):
+        assert f"ok  {group}" in r.stdout, group
+
+
+def test_emulation_catches_a_broken_exchange_protocol(tmp_path):
+    """Mutation check of the cross-rank protocol: with ONE slot parity a rank that ran a call ahead overwrites the record
+    a slow peer is still reading -- the emulated ranks (one OS thread each, the last one a slow reader) must see it."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not installed")
+    mutated = tmp_path / "csrc"
+    mutated.mkdir()
+    for h in os.listdir(CSRC):
+        if h.endswith(".cuh"):
+            shutil.copy(os.path.join(CSRC, h), mutated / h)
+    src = (mutated / "merge_kernels.cuh").read_text()
+    needle = "const int parity = int(epoch & 1);"
+    assert src.count(needle) == 1
+    (mutated / "merge_kernels.cuh").write_text(src.replace(needle, "const int parity = 0;"))
+    exe = _build_kernel_test(mutated, tmp_path / "mutant")
+    r = subprocess.run([str(exe), "1"], capture_output=True, text=True, timeout=900)
+    assert r.returncode != 0 and "FAILED" in r.stderr and "exchange" in r.stderr

@@ -34,7 +34,13 @@ static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
-template <class T> static inline T __ldcv(const T* p) { return *static_cast<const volatile T*>(p); }
+template <class T> static inline T __ldcv(const T* p) {
+  if (warp_emu::nap_us() && warp_emu::nap_armed()) {       // fault injection, see warp_emu::nap_us()
+    warp_emu::nap_armed() = false;
+    std::this_thread::sleep_for(std::chrono::microseconds(warp_emu::nap_us()));
+  }
+  return *static_cast<const volatile T*>(p);
+}
 
 // fibers of one block never run at the same time, so a read-modify-write is atomic among them
 template <class T> static inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }

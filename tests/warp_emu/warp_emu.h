@@ -1,5 +1,5 @@
 // CUDA thread blocks on the CPU, for the pure-SIMT parts of the search kernels.  Every CUDA thread of one block is a
-// ucontext fiber; fibers run one at a time and switch only at synchronisation points, so plain arrays behave like
+// fiber (its own stack, switched in user space); fibers run one at a time and switch only at synchronisation points, so plain arrays behave like
 // shared memory between barriers:
 //   * a warp collective (shuffle, ballot, reduction, match, __syncwarp) is a barrier of the 32 lanes of one warp at
 //     which values are handed over through a slot array;
@@ -24,8 +24,42 @@ namespace warp_emu {
 constexpr int kLanes = 32;
 constexpr size_t kStackBytes = 512 << 10;
 
+// Context switch between fibers.  x86-64: a dozen instructions that swap the callee-saved registers and the stack
+// pointer (glibc's swapcontext makes two sigprocmask system calls per switch, and the kernels below switch millions of
+// times); elsewhere: ucontext.
+#if defined(__x86_64__) && !defined(WARP_EMU_USE_UCONTEXT)
+#define WARP_EMU_FAST_SWITCH 1
+extern "C" void warp_emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.weak warp_emu_switch
+.type warp_emu_switch,@function
+warp_emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size warp_emu_switch,.-warp_emu_switch
+)");
+#endif
+
 struct Fiber {
+#ifdef WARP_EMU_FAST_SWITCH
+  void* sp = nullptr;
+#else
   ucontext_t ctx;
+#endif
   char* stack = nullptr;
   bool done = false;
 };
@@ -37,7 +71,11 @@ struct WarpState {
 };
 
 struct Block {
+#ifdef WARP_EMU_FAST_SWITCH
+  void* main_sp = nullptr;
+#else
   ucontext_t main;
+#endif
   std::vector<Fiber> fibers;
   std::vector<WarpState> warps;
   int n_threads = 0, live = 0;
@@ -55,6 +93,18 @@ inline uint64_t& spin_count() {
   return n;
 }
 
+// Fault injection for protocol tests: when nap_us() is set on an OS thread, the FIRST volatile load (__ldcv) of every
+// block it runs sleeps that long -- in the exchange kernel that is the moment a rank starts reading the records its
+// peers pushed, i.e. the window in which a peer that ran ahead must not be able to overwrite them.
+inline int& nap_us() {
+  static thread_local int us = 0;
+  return us;
+}
+inline bool& nap_armed() {
+  static thread_local bool armed = false;
+  return armed;
+}
+
 inline Block*& current() {
   static thread_local Block* b = nullptr;
   return b;
@@ -69,7 +119,11 @@ inline int lane() { return current()->cur & (kLanes - 1); }
 
 inline void yield_thread() {
   Block* b = current();
+#ifdef WARP_EMU_FAST_SWITCH
+  warp_emu_switch(&b->fibers[b->cur].sp, b->main_sp);
+#else
   swapcontext(&b->fibers[b->cur].ctx, &b->main);
+#endif
 }
 
 inline void barrier() {            // the 32 lanes of the calling thread's warp
@@ -151,6 +205,9 @@ inline void trampoline() {
   ++b->progress;
   if (w.arrived > 0 && w.arrived >= w.live) { w.arrived = 0; ++w.gen; }
   if (b->bar_arrived > 0 && b->bar_arrived >= b->live) { b->bar_arrived = 0; ++b->bar_gen; }
+#ifdef WARP_EMU_FAST_SWITCH
+  for (;;) yield_thread();       // a finished fiber has no frame to return to; the scheduler never resumes it
+#endif
 }
 
 // one thread block of n_threads CUDA threads (a multiple of 32), all running body() to completion
@@ -160,6 +217,7 @@ inline void run_block(int n_threads, unsigned block_index, unsigned grid, const 
   Block* outer = current();
   current() = b;
   b->body = body;
+  nap_armed() = true;
   b->n_threads = b->live = n_threads;
   b->block_idx = block_index;
   b->grid_dim = grid;
@@ -169,11 +227,22 @@ inline void run_block(int n_threads, unsigned block_index, unsigned grid, const 
   for (int t = 0; t < n_threads; ++t) {
     Fiber& f = b->fibers[t];
     f.stack = static_cast<char*>(malloc(kStackBytes));
+#ifdef WARP_EMU_FAST_SWITCH
+    // initial frame: six callee-saved registers, then the entry point as the address `ret` jumps to, then a dummy
+    // return address so the entry function sees the stack alignment of an ordinary call
+    uintptr_t top = (reinterpret_cast<uintptr_t>(f.stack) + kStackBytes) & ~uintptr_t(15);
+    void** frame = reinterpret_cast<void**>(top) - 8;
+    for (int i = 0; i < 6; ++i) frame[i] = nullptr;
+    frame[6] = reinterpret_cast<void*>(&trampoline);
+    frame[7] = nullptr;
+    f.sp = frame;
+#else
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = f.stack;
     f.ctx.uc_stack.ss_size = kStackBytes;
     f.ctx.uc_link = &b->main;
     makecontext(&f.ctx, reinterpret_cast<void (*)()>(trampoline), 0);
+#endif
   }
   int stuck_sweeps = 0;
   uint64_t spinning_sweeps = 0;
@@ -186,7 +255,11 @@ inline void run_block(int n_threads, unsigned block_index, unsigned grid, const 
     for (int t = 0; t < n_threads; ++t) {
       if (b->fibers[t].done) continue;
       b->cur = t;
+#ifdef WARP_EMU_FAST_SWITCH
+      warp_emu_switch(&b->main_sp, b->fibers[t].sp);
+#else
       swapcontext(&b->main, &b->fibers[t].ctx);
+#endif
     }
     int warp_arrived_after = 0;
     for (auto& w : b->warps) warp_arrived_after += w.arrived;
