@@ -1,9 +1,11 @@
-"""The SIMT parts of the search kernels on the CPU.  csrc/topk.cuh, pool_floor.cuh, merge_kernels.cuh and
-rank_kernels.cuh hold no tcgen05 / TMA / mbarrier code, so the SAME headers the library compiles are compiled for the
+"""The SIMT parts of the kernels on the CPU.  csrc/topk.cuh, pool_floor.cuh, merge_kernels.cuh, rank_kernels.cuh and
+encoder_simt.cuh hold no tcgen05 / TMA / mbarrier code, so the SAME headers the library compiles are compiled for the
 host with CUDA threads as fibers (tests/warp_emu: warp collectives, __syncthreads, shared memory, one OS thread per
 rank with real atomics for the cross-rank exchange) and checked against plain C++ models:
   selector_emu_test.cpp  bitonic sort, flush / insert list maintenance, select_stream, and the pooled admission
                          floors -- above all the property exactness rests on: >= k published keys reach the floor
+  encoder_emu_test.cpp   embedding + LayerNorm, LayerNorm, masked mean pool + L2 normalise (K3) and the classifier
+                         head (csrc/encoder_simt.cuh) against double-precision models
   kernel_emu_test.cpp    the radix-rank kernels (full permutation == stable descending sort), merge_topk_kernel in
                          both layouts, and finalize_exchange_kernel on 2 / 3 / 4 / 8 ranks, calls back to back with
                          a deliberately slow reader (the slot-parity protocol)."""
@@ -112,3 +114,22 @@ def test_emulation_catches_a_broken_exchange_protocol(tmp_path):
     exe = _build_kernel_test(mutated, tmp_path / "mutant")
     r = subprocess.run([str(exe), "1"], capture_output=True, text=True, timeout=900)
     assert r.returncode != 0 and "FAILED" in r.stderr and "exchange" in r.stderr
+
+
+def test_encoder_simt_kernels_on_emulated_blocks(tmp_path):
+    """embed_layernorm / layernorm / pool_normalize (BGEEmbedding.py:15-28, :127) / cls_head from csrc/encoder_simt.cuh,
+    the file encoder_kernels.cu includes, against double-precision models (bf16 outputs within one bf16 step, fp32
+    outputs within 2e-6)."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not installed")
+    assert '#include "encoder_simt.cuh"' in open(os.path.join(CSRC, "encoder_kernels.cu")).read()
+    exe = tmp_path / "encoder_emu_test"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wno-unknown-pragmas", "-pthread", "-I", os.path.join(EMU, "stub"), "-I", CSRC,
+                        os.path.join(EMU, "encoder_emu_test.cpp"), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("ALL OK")
+    for group in ("layernorm_kernel<4>: H = 1024", "embed_layernorm_kernel<4>: H = 1024, position offset 2",
+                  "pool_normalize_kernel: H = 1024", "cls_head_kernel: H = 1024"):
+        assert f"ok  {group}" in r.stdout, group

@@ -27,6 +27,17 @@
 #define blockDim (warp_emu::block_dim())
 #define gridDim (warp_emu::grid_dim())
 
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }   // the GPU's rsqrt.approx is within 2 ulp of this
+
+// csrc/encoder_simt.cuh: dynamic shared memory and its one named barrier
+#define CRAG_DYNAMIC_SHARED(type, name) type* name = static_cast<type*>(warp_emu::dynamic_shared())
+namespace crag {
+static inline void bar_sync_group0_128() { warp_emu::named_barrier(1, 128); }
+}  // namespace crag
+
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }

@@ -81,6 +81,9 @@ struct Block {
   int n_threads = 0, live = 0;
   int bar_arrived = 0;
   uint64_t bar_gen = 0;
+  int named_arrived[16] = {0};   // bar.sync <id>, <count>: barriers over a fixed number of threads
+  uint64_t named_gen[16] = {0};
+  std::vector<uint8_t> dyn_smem;  // the launch's dynamic shared memory (garbage-filled: CUDA does not zero it)
   uint64_t progress = 0;        // bumps whenever any barrier releases or a thread exits (deadlock detection)
   int cur = 0;
   unsigned block_idx = 0, grid_dim = 1;
@@ -149,6 +152,19 @@ inline void sync_block() {         // __syncthreads()
   while (b->bar_gen == my) yield_thread();
 }
 
+inline void named_barrier(int id, int count) {     // bar.sync id, count
+  Block* b = current();
+  const uint64_t my = b->named_gen[id];
+  if (++b->named_arrived[id] >= count) {
+    b->named_arrived[id] = 0;
+    ++b->named_gen[id];
+    ++b->progress;
+  }
+  while (b->named_gen[id] == my) yield_thread();
+}
+
+inline void* dynamic_shared() { return current()->dyn_smem.data(); }
+
 // every lane deposits v; lane l receives the value of lane src_of(l)
 template <class T, class F>
 inline T exchange(T v, F src_of) {
@@ -211,12 +227,14 @@ inline void trampoline() {
 }
 
 // one thread block of n_threads CUDA threads (a multiple of 32), all running body() to completion
-inline void run_block(int n_threads, unsigned block_index, unsigned grid, const std::function<void()>& body) {
+inline void run_block(int n_threads, unsigned block_index, unsigned grid, const std::function<void()>& body,
+                      size_t dynamic_smem_bytes = 0) {
   if (n_threads % kLanes != 0) { fprintf(stderr, "warp_emu: block size must be a multiple of 32\n"); abort(); }
   Block* b = new Block;
   Block* outer = current();
   current() = b;
   b->body = body;
+  b->dyn_smem.assign(dynamic_smem_bytes + 16, 0xCD);
   nap_armed() = true;
   b->n_threads = b->live = n_threads;
   b->block_idx = block_index;
@@ -252,6 +270,7 @@ inline void run_block(int n_threads, unsigned block_index, unsigned grid, const 
     const int arrived_before = b->bar_arrived;
     int warp_arrived_before = 0;
     for (auto& w : b->warps) warp_arrived_before += w.arrived;
+    for (int i = 0; i < 16; ++i) warp_arrived_before += b->named_arrived[i];
     for (int t = 0; t < n_threads; ++t) {
       if (b->fibers[t].done) continue;
       b->cur = t;
@@ -263,6 +282,7 @@ inline void run_block(int n_threads, unsigned block_index, unsigned grid, const 
     }
     int warp_arrived_after = 0;
     for (auto& w : b->warps) warp_arrived_after += w.arrived;
+    for (int i = 0; i < 16; ++i) warp_arrived_after += b->named_arrived[i];
     if (b->progress == before && b->bar_arrived == arrived_before && warp_arrived_after == warp_arrived_before && b->live > 0) {
       // nothing moved in a whole sweep.  Threads sleeping in a spin-wait on memory another OS thread will write (the
       // exchange kernel's flag wait) are legitimate and get a long leash; anything else is a lost collective.
@@ -282,8 +302,8 @@ inline void run_block(int n_threads, unsigned block_index, unsigned grid, const 
 }
 
 // kernel<<<grid, block>>>: blocks run one after the other
-inline void launch(unsigned grid, int block, const std::function<void()>& kernel_call) {
-  for (unsigned bidx = 0; bidx < grid; ++bidx) run_block(block, bidx, grid, kernel_call);
+inline void launch(unsigned grid, int block, const std::function<void()>& kernel_call, size_t dynamic_smem_bytes = 0) {
+  for (unsigned bidx = 0; bidx < grid; ++bidx) run_block(block, bidx, grid, kernel_call, dynamic_smem_bytes);
 }
 
 // one warp, body(lane): what the selector-primitive tests use
