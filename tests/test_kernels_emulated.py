@@ -6,7 +6,8 @@ rank with real atomics for the cross-rank exchange) and checked against plain C+
                          floors -- above all the property exactness rests on: >= k published keys reach the floor
   encoder_emu_test.cpp   embedding + LayerNorm, LayerNorm, masked mean pool + L2 normalise (K3) and the classifier
                          head (csrc/encoder_simt.cuh) against double-precision models
-  kernel_emu_test.cpp    the radix-rank kernels (full permutation == stable descending sort), merge_topk_kernel in
+  kernel_emu_test.cpp    the IVF plan / id-map kernels, the radix-rank kernels (full permutation == stable descending
+                         sort), merge_topk_kernel in
                          both layouts, and finalize_exchange_kernel on 2 / 3 / 4 / 8 ranks, calls back to back with
                          a deliberately slow reader (the slot-parity protocol)."""
 import os
@@ -92,7 +93,7 @@ def test_rank_merge_and_exchange_kernels_on_emulated_blocks(kernel_binary):
     r = subprocess.run([str(kernel_binary), "1"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip().endswith("ALL OK")
-    for group in ("rank kernels: n = 6000", "merge_topk_kernel<128, 128, keys>", "merge_topk_kernel<64, 64, packed records>",
+    for group in ("ivf_plan_kernel + ivf_map_ids_kernel: nlist = 4096", "rank kernels: n = 6000", "merge_topk_kernel<128, 128, keys>", "merge_topk_kernel<64, 64, packed records>",
                   "finalize_exchange_kernel<64, 64>: world = 3", "finalize_exchange_kernel<128, 128>: world = 8"):
         assert f"ok  {group}" in r.stdout, group
 

@@ -2,6 +2,8 @@
 // includes (csrc/rank_kernels.cuh, merge_kernels.cuh):
 //   rank     hist / scan / scatter kernels, driven pass by pass exactly as crag_rank_scores drives them, against
 //            std::stable_sort -- the full permutation of ComoRAG.py:965-966 (descending score, ascending row on ties)
+//   ivf      ivf_plan_kernel (query masks, coarse terms, work-list of probed tiles) and ivf_map_ids_kernel against a direct
+//            restatement of oracle/ivf_oracle.py's plan
 //   merge    merge_topk_kernel, both input layouts (per-CTA key lists; packed per-shard (id, score) records)
 //   exchange finalize_exchange_kernel with `world` ranks, ONE OS THREAD PER RANK pushing into each other's buffers
 //            through release / acquire flags, several calls in a row (slot parity reuse): every rank must end with the
@@ -16,6 +18,7 @@
 
 #include <cuda_runtime.h>   // the stub
 
+#include "ivf_kernels.cuh"
 #include "merge_kernels.cuh"
 #include "rank_kernels.cuh"
 
@@ -80,6 +83,65 @@ static void test_rank(int64_t n, int levels, bool specials) {
   }
   printf("ok  rank kernels: n = %lld (%d warps, %d blocks), %s: permutation == stable descending sort, scores bit-equal\n",
          (long long)n, p.n_warps, p.grid, levels ? "heavy ties" : "random scores");
+}
+
+// -------------------------------------------------------------------------------------------------------- ivf
+#include <map>
+#include <set>
+#include <tuple>
+static void test_ivf_plan(int nlist, int nq, int nprobe) {
+  std::vector<int32_t> list_rows(nlist), list_tile_start(nlist + 1, 0);
+  for (int l = 0; l < nlist; ++l) {
+    list_rows[l] = (rng() % 6 == 0) ? 0 : int(rng() % 700);               // some lists are empty
+    list_tile_start[l + 1] = list_tile_start[l] + (list_rows[l] + kTileRows - 1) / kTileRows;
+  }
+  std::vector<int64_t> probed(size_t(nq) * nprobe);
+  std::vector<float> pscore(size_t(nq) * nprobe);
+  for (int q = 0; q < nq; ++q) {
+    std::vector<int> perm(nlist);
+    for (int l = 0; l < nlist; ++l) perm[l] = l;
+    std::shuffle(perm.begin(), perm.end(), rng);
+    for (int j = 0; j < nprobe; ++j) {
+      const bool absent = j >= nlist || rng() % 11 == 0;                  // fewer than nprobe lists: id -1
+      probed[size_t(q) * nprobe + j] = absent ? -1 : perm[j];
+      pscore[size_t(q) * nprobe + j] = random_score(0);
+    }
+  }
+  std::vector<uint32_t> mask(nlist, 0xFFFFFFFFu);
+  std::vector<float> coarse(size_t(nlist) * kNQ, -77.f);
+  std::vector<int4> work(size_t(list_tile_start[nlist]) + 1, int4{-1, -1, -1, -1});
+  int n_work = -1;
+  warp_emu::launch(1, 1024, [&] {
+    ivf_plan_kernel(probed.data(), pscore.data(), nq, nprobe, nlist, list_tile_start.data(), list_rows.data(), mask.data(), coarse.data(), work.data(), &n_work);
+  });
+  std::vector<uint32_t> want_mask(nlist, 0u);
+  std::map<std::pair<int, int>, float> want_coarse;
+  for (int q = 0; q < nq; ++q)
+    for (int j = 0; j < nprobe; ++j) {
+      const int64_t l = probed[size_t(q) * nprobe + j];
+      if (l < 0) continue;
+      want_mask[l] |= 1u << q;
+      want_coarse[{int(l), q}] = pscore[size_t(q) * nprobe + j];
+    }
+  std::set<std::tuple<int, int, int>> want_work, got_work;
+  for (int l = 0; l < nlist; ++l) {
+    REQUIRE(mask[l] == want_mask[l], "ivf plan: mask of list %d", l);
+    if (!want_mask[l] || list_rows[l] <= 0) continue;
+    for (int j = 0; j * kTileRows < list_rows[l]; ++j)
+      want_work.insert({(list_tile_start[l] + j) * kTileRows, std::min(kTileRows, list_rows[l] - j * kTileRows), l});
+  }
+  for (auto& kv : want_coarse) REQUIRE(coarse[size_t(kv.first.first) * kNQ + kv.first.second] == kv.second, "ivf plan: coarse term list %d query %d", kv.first.first, kv.first.second);
+  REQUIRE(n_work == int(want_work.size()), "ivf plan: %d work items, want %zu", n_work, want_work.size());
+  for (int i = 0; i < n_work; ++i) got_work.insert({work[i].x, work[i].y, work[i].z});
+  REQUIRE(got_work == want_work, "ivf plan: work-list differs (nlist %d nq %d nprobe %d)", nlist, nq, nprobe);
+  // merged answer's stored-row ids -> original ids
+  std::vector<int64_t> row_ids(1000), ids(300);
+  for (size_t i = 0; i < row_ids.size(); ++i) row_ids[i] = (i % 9 == 0) ? -1 : int64_t(rng() % (int64_t(1) << 40));
+  std::vector<int64_t> before(ids.size());
+  for (size_t i = 0; i < ids.size(); ++i) before[i] = ids[i] = (i % 7 == 0) ? -1 : int64_t(rng() % row_ids.size());
+  warp_emu::launch((unsigned(ids.size()) + 255) / 256, 256, [&] { ivf_map_ids_kernel(ids.data(), int(ids.size()), row_ids.data()); });
+  for (size_t i = 0; i < ids.size(); ++i) REQUIRE(ids[i] == (before[i] >= 0 ? row_ids[before[i]] : -1), "ivf id map at %zu", i);
+  printf("ok  ivf_plan_kernel + ivf_map_ids_kernel: nlist = %d, %d queries x %d probes, %d work items\n", nlist, nq, nprobe, n_work);
 }
 
 // ------------------------------------------------------------------------------------------------------ merge
@@ -291,6 +353,9 @@ int main(int argc, char** argv) {
   test_rank(4097, 0, true);
   test_rank(6000, 3, true);
   if (scale > 1) test_rank(20000, 5, true);
+  test_ivf_plan(64, 32, 8);
+  test_ivf_plan(4096, 32, 32);
+  test_ivf_plan(10, 5, 16);
   test_merge_keys<32, 32>(6 * scale);
   test_merge_keys<64, 64>(6 * scale);
   test_merge_keys<128, 128>(6 * scale);

@@ -30,6 +30,9 @@
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct alignas(16) int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+static inline int min(int a, int b) { return a < b ? a : b; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }   // the GPU's rsqrt.approx is within 2 ulp of this
 
 // csrc/encoder_simt.cuh: dynamic shared memory and its one named barrier
@@ -55,6 +58,7 @@ template <class T> static inline T __ldcv(const T* p) {
 
 // fibers of one block never run at the same time, so a read-modify-write is atomic among them
 template <class T> static inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }
+template <class T> static inline T atomicOr(T* p, T v) { T old = *p; *p = old | v; return old; }
 
 static inline void __syncthreads() { warp_emu::sync_block(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { warp_emu::barrier(); }
