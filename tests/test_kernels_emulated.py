@@ -4,6 +4,10 @@ host with CUDA threads as fibers (tests/warp_emu: warp collectives, __syncthread
 rank with real atomics for the cross-rank exchange) and checked against plain C++ models:
   selector_emu_test.cpp  bitonic sort, flush / insert list maintenance, select_stream, and the pooled admission
                          floors -- above all the property exactness rests on: >= k published keys reach the floor
+  select_emu_test.cpp    the SELECT WARPS of the headline kernel (csrc/select_warps.inc.cuh, the text search_topk_kernel
+                         #includes): admission, warp-ballot compaction, flushes, pooled-floor refreshes across CTAs,
+                         drain, rank continuation, score-all and IVF variants -- fed a score matrix in place of
+                         tcgen05.ld, merged by the emulated merge kernel, compared bit for bit with the exact top-k
   encoder_emu_test.cpp   embedding + LayerNorm, LayerNorm, masked mean pool + L2 normalise (K3) and the classifier
                          head (csrc/encoder_simt.cuh) against double-precision models
   kernel_emu_test.cpp    the IVF plan / id-map kernels, the radix-rank kernels (full permutation == stable descending
@@ -139,3 +143,47 @@ def test_encoder_simt_kernels_on_emulated_blocks(tmp_path):
     for group in ("layernorm_kernel<4>: H = 1024", "embed_layernorm_kernel<4>: H = 1024, position offset 2",
                   "pool_normalize_kernel: H = 1024", "cls_head_kernel: H = 1024"):
         assert f"ok  {group}" in r.stdout, group
+
+
+def _build_select_test(csrc_dir, exe):
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wno-unknown-pragmas", "-pthread", "-I", os.path.join(EMU, "stub"), "-I", str(csrc_dir),
+                        os.path.join(EMU, "select_emu_test.cpp"), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_select_warps_of_the_scan_kernel_on_emulated_blocks(tmp_path):
+    """search_topk_kernel's select warps -- the text the kernel itself #includes -- on adversarial score matrices
+    (ascending with the row id, all rows equal, three score levels, planted neighbours in the tail, random), k from 1
+    to 128, 1 to 148 CTAs sharing the pooled floor, with and without the tile permutation; rank continuation over
+    several pages; the score-all and IVF variants.  Ids, scores and (min, max) must equal the exact answer."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not installed")
+    kernel_src = open(os.path.join(CSRC, "search.cu")).read()
+    assert kernel_src.count('#include "select_warps.inc.cuh"') == 3      # the kernel is built from the very same text
+    exe = _build_select_test(CSRC, tmp_path / "select_emu_test")
+    r = subprocess.run([str(exe), "1"], capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("ALL OK")
+    for group in ("select warps <64, 64>: all rows equal", "select warps <128, 128>: planted neighbours in the last rows, 75699 rows on 148 CTAs",
+                  "rank continuation <128, 128>: random", "IVF variant <128, 128>: 64 lists", "score-all variant: 4475 rows"):
+        assert f"ok  {group}" in r.stdout, group
+
+
+def test_emulation_catches_a_selector_that_drops_a_tie(tmp_path):
+    """Mutation check: an admission test that compares scores only (strictly) loses rows that tie the k-th score with a
+    smaller row id -- the all-equal / few-levels corpora and the continuation pages must expose it."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not installed")
+    mutated = tmp_path / "csrc"
+    mutated.mkdir()
+    for h in os.listdir(CSRC):
+        if h.endswith(".cuh"):
+            shutil.copy(os.path.join(CSRC, h), mutated / h)
+    src = (mutated / "select_warps.inc.cuh").read_text()
+    needle = "if (s >= thr_f[q] && s <= bnd_f[q] && make_key(s, uint32_t(row)) > thr_key[q]) pending |= 1u << q;"
+    assert src.count(needle) == 2          # flat and IVF admission
+    (mutated / "select_warps.inc.cuh").write_text(src.replace(needle, "if (s > thr_f[q] && s <= bnd_f[q]) pending |= 1u << q;"))
+    exe = _build_select_test(mutated, tmp_path / "mutant")
+    r = subprocess.run([str(exe), "ties"], capture_output=True, text=True, timeout=1800)
+    assert r.returncode != 0 and "FAILED" in r.stderr

@@ -83,6 +83,7 @@ struct Block {
   uint64_t bar_gen = 0;
   int named_arrived[16] = {0};   // bar.sync <id>, <count>: barriers over a fixed number of threads
   uint64_t named_gen[16] = {0};
+  bool named_or_acc[16] = {false}, named_or_result[16] = {false};
   std::vector<uint8_t> dyn_smem;  // the launch's dynamic shared memory (garbage-filled: CUDA does not zero it)
   uint64_t progress = 0;        // bumps whenever any barrier releases or a thread exits (deadlock detection)
   int cur = 0;
@@ -161,6 +162,22 @@ inline void named_barrier(int id, int count) {     // bar.sync id, count
     ++b->progress;
   }
   while (b->named_gen[id] == my) yield_thread();
+}
+
+// barrier.cta.red.or: named barrier whose threads also learn the OR of everybody's predicate
+inline bool named_barrier_or(int id, int count, bool pred) {
+  Block* b = current();
+  const uint64_t my = b->named_gen[id];
+  b->named_or_acc[id] = b->named_or_acc[id] || pred;
+  if (++b->named_arrived[id] >= count) {
+    b->named_or_result[id] = b->named_or_acc[id];
+    b->named_or_acc[id] = false;
+    b->named_arrived[id] = 0;
+    ++b->named_gen[id];
+    ++b->progress;
+  }
+  while (b->named_gen[id] == my) yield_thread();
+  return b->named_or_result[id];   // stable until every participant has left: the next release needs all of them again
 }
 
 inline void* dynamic_shared() { return current()->dyn_smem.data(); }
