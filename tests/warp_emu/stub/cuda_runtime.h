@@ -57,7 +57,7 @@ template <class T> static inline T __ldcv(const T* p) {
 }
 
 // fibers of one block never run at the same time, so a read-modify-write is atomic among them
-template <class T> static inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }
+template <class T> static inline T atomicAdd(T* p, T v) { ++warp_emu::census().atomics; T old = *p; *p = old + v; return old; }
 template <class T> static inline T atomicOr(T* p, T v) { T old = *p; *p = old | v; return old; }
 
 static inline void __syncthreads() { warp_emu::sync_block(); }
@@ -70,12 +70,15 @@ static inline void __nanosleep(unsigned) {
 }
 
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+  ++warp_emu::census().shuffles;
   return warp_emu::exchange(v, [&](int lane) { return lane ^ lane_mask; });
 }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
+  ++warp_emu::census().shuffles;
   return warp_emu::exchange(v, [&](int) { return src & 31; });
 }
 static inline unsigned __ballot_sync(unsigned, int pred) {
+  ++warp_emu::census().ballots;
   return warp_emu::reduce<unsigned>(pred ? (1u << warp_emu::lane()) : 0u, [](unsigned a, unsigned b) { return a | b; });
 }
 static inline unsigned __match_any_sync(unsigned, unsigned v) {
@@ -86,11 +89,11 @@ static inline unsigned __match_any_sync(unsigned, unsigned v) {
     return m;
   });
 }
-static inline int __reduce_add_sync(unsigned, int v) { return warp_emu::reduce<int>(v, [](int a, int b) { return a + b; }); }
-static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return warp_emu::reduce<unsigned>(v, [](unsigned a, unsigned b) { return a + b; }); }
-static inline unsigned __reduce_min_sync(unsigned, unsigned v) { return warp_emu::reduce<unsigned>(v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
-static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return warp_emu::reduce<unsigned>(v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
-static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return warp_emu::reduce<unsigned>(v, [](unsigned a, unsigned b) { return a | b; }); }
+static inline int __reduce_add_sync(unsigned, int v) { ++warp_emu::census().reductions; return warp_emu::reduce<int>(v, [](int a, int b) { return a + b; }); }
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) { ++warp_emu::census().reductions; return warp_emu::reduce<unsigned>(v, [](unsigned a, unsigned b) { return a + b; }); }
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) { ++warp_emu::census().reductions; return warp_emu::reduce<unsigned>(v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) { ++warp_emu::census().reductions; return warp_emu::reduce<unsigned>(v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
+static inline unsigned __reduce_or_sync(unsigned, unsigned v) { ++warp_emu::census().reductions; return warp_emu::reduce<unsigned>(v, [](unsigned a, unsigned b) { return a | b; }); }
 
 // the inline-PTX wrappers of csrc/merge_kernels.cuh (st.release.sys / ld.acquire.sys / %globaltimer)
 namespace crag {

@@ -91,6 +91,16 @@ struct Block {
   std::function<void()> body;
 };
 
+// How often each kind of warp-level operation ran on this OS thread (every lane counts its own call): lets a tool say
+// what the select warps spend their instructions on (tests/warp_emu/select_census.cpp).
+struct Census {
+  uint64_t shuffles = 0, reductions = 0, ballots = 0, named_barriers = 0, atomics = 0;
+};
+inline Census& census() {
+  static thread_local Census c;
+  return c;
+}
+
 // bumped by the __nanosleep stand-in: a thread that sleeps is waiting for memory ANOTHER OS thread will write
 inline uint64_t& spin_count() {
   static thread_local uint64_t n = 0;
@@ -155,6 +165,7 @@ inline void sync_block() {         // __syncthreads()
 
 inline void named_barrier(int id, int count) {     // bar.sync id, count
   Block* b = current();
+  ++census().named_barriers;
   const uint64_t my = b->named_gen[id];
   if (++b->named_arrived[id] >= count) {
     b->named_arrived[id] = 0;
@@ -167,6 +178,7 @@ inline void named_barrier(int id, int count) {     // bar.sync id, count
 // barrier.cta.red.or: named barrier whose threads also learn the OR of everybody's predicate
 inline bool named_barrier_or(int id, int count, bool pred) {
   Block* b = current();
+  ++census().named_barriers;
   const uint64_t my = b->named_gen[id];
   b->named_or_acc[id] = b->named_or_acc[id] || pred;
   if (++b->named_arrived[id] >= count) {
