@@ -146,7 +146,7 @@ def test_encoder_simt_kernels_on_emulated_blocks(tmp_path):
 
 
 def _build_select_test(csrc_dir, exe):
-    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wno-unknown-pragmas", "-pthread", "-I", os.path.join(EMU, "stub"), "-I", str(csrc_dir),
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wno-unknown-pragmas", "-pthread", "-I", os.path.join(EMU, "stub"), "-I", str(csrc_dir),
                         os.path.join(EMU, "select_emu_test.cpp"), "-o", str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return exe
@@ -155,7 +155,8 @@ def _build_select_test(csrc_dir, exe):
 def test_select_warps_of_the_scan_kernel_on_emulated_blocks(tmp_path):
     """search_topk_kernel's select warps -- the text the kernel itself #includes -- on adversarial score matrices
     (ascending with the row id, all rows equal, three score levels, planted neighbours in the tail, random), k from 1
-    to 128, 1 to 148 CTAs sharing the pooled floor, with and without the tile permutation; rank continuation over
+    to 128, 1 to 148 CTAs sharing the pooled floor -- run one after the other and all resident together in random
+    interleavings --, with and without the tile permutation; rank continuation over
     several pages; the score-all and IVF variants.  Ids, scores and (min, max) must equal the exact answer."""
     if shutil.which("g++") is None:
         pytest.skip("g++ not installed")
@@ -166,6 +167,7 @@ def test_select_warps_of_the_scan_kernel_on_emulated_blocks(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip().endswith("ALL OK")
     for group in ("select warps <64, 64>: all rows equal", "select warps <128, 128>: planted neighbours in the last rows, 75699 rows on 148 CTAs",
+                  "select warps <128, 128>: all rows equal, 75699 rows on 148 CTAs (4 tiles each), nq = 32, k = 100, pool on, permutation on, CTAs interleaved",
                   "rank continuation <128, 128>: random", "IVF variant <128, 128>: 64 lists", "score-all variant: 4475 rows"):
         assert f"ok  {group}" in r.stdout, group
 

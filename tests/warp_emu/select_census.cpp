@@ -2,7 +2,7 @@
 // (select_shell.h): how many warp shuffles (the bitonic sorts), warp reductions (the pooled-floor bisections), ballots
 // and shared-memory atomics (candidate reservations) and named barriers one select warp executes per scan.  Not a
 // timing -- an instruction-class count that says where a fixed cost can come from.
-//   select_census ROWS K [NQ]        e.g. 1250000 100   (one rank's shard of the 8-GPU split, config 4's k)
+//   select_census ROWS K [NQ [CONCURRENT]]   e.g. 1250000 100 32 1   (one rank's shard of the 8-GPU split, config 4's k)
 // Random unit-variance scores (the regime of a random corpus: admissions are rare once the floor has converged).
 #include <cstdio>
 #include <cstdlib>
@@ -23,7 +23,7 @@ static uint32_t perm_multiplier(int64_t groups) {
 }
 
 template <int KLIST, int CAP, int STAGES>
-static void census(int64_t rows, int k, int nq, int grid) {
+static void census(int64_t rows, int k, int nq, int grid, bool concurrent) {
   std::mt19937_64 rng(5);
   std::normal_distribution<float> nd(0.f, 0.03125f);     // q . x of unit vectors at dim 1024
   std::vector<float> scores(size_t(rows) * kNQ);
@@ -35,19 +35,21 @@ static void census(int64_t rows, int k, int nq, int grid) {
   const int shift = 3;
   const uint32_t perm = perm_multiplier(tiles >> shift);
   warp_emu::census() = warp_emu::Census{};
-  warp_emu::launch(grid, kSearchThreads, [&] {
+  auto scan = [&] {
     search_select_shell<KLIST, CAP, STAGES>(int(rows), nq, k, nullptr, pool.data(), perm, shift, part_keys.data(), part_mm.data(), NoIvfArgs{});
-  });
+  };
+  if (concurrent) warp_emu::launch_concurrent(grid, kSearchThreads, scan, select_shell_smem_bytes<KLIST, CAP>(), 7);
+  else warp_emu::launch(grid, kSearchThreads, scan, select_shell_smem_bytes<KLIST, CAP>());
   const warp_emu::Census c = warp_emu::census();
   const double warps = double(grid) * 4.0, lanes = warps * 32.0;
   const double tiles_per_cta = double(tiles) / grid;
   // a 256-key sort (KLIST + CAP = 256) is 15 cross-lane stages x 8 keys x 2 shuffles = 240 shuffles per lane, a 128-key
   // sort 120; the (min, max) reduction at the end adds 32 x 5 x 2 = 320 per lane
   const double shf = double(c.shuffles) / lanes;
-  printf("{\"rows\": %lld, \"k\": %d, \"nq\": %d, \"ctas\": %d, \"tiles_per_cta\": %.1f, \"selector\": \"<%d, %d>\",\n"
+  printf("{\"rows\": %lld, \"k\": %d, \"nq\": %d, \"ctas\": %d, \"ctas_run\": \"%s\", \"tiles_per_cta\": %.1f, \"selector\": \"<%d, %d>\",\n"
          " \"per_select_warp\": {\"shuffles_per_lane\": %.0f, \"equivalent_%d_key_sorts\": %.1f, \"warp_reductions\": %.0f, \"ballots\": %.0f,\n"
          "                     \"shared_atomics_per_warp\": %.0f, \"named_barriers_per_thread\": %.0f}}\n",
-         (long long)rows, k, nq, grid, tiles_per_cta, KLIST, CAP, shf, KLIST + CAP, (shf - 320.0) / (KLIST + CAP == 256 ? 240.0 : 120.0),
+         (long long)rows, k, nq, grid, concurrent ? "interleaved (all resident)" : "one after the other", tiles_per_cta, KLIST, CAP, shf, KLIST + CAP, (shf - 320.0) / (KLIST + CAP == 256 ? 240.0 : 120.0),
          double(c.reductions) / lanes, double(c.ballots) / lanes, double(c.atomics) / warps, double(c.named_barriers) / (warps * 32.0));
 }
 
@@ -55,7 +57,8 @@ int main(int argc, char** argv) {
   const int64_t rows = argc > 1 ? atoll(argv[1]) : 1250000;
   const int k = argc > 2 ? atoi(argv[2]) : 100;
   const int nq = argc > 3 ? atoi(argv[3]) : 32;
-  if (k <= 64) census<64, 64, 7>(rows, k, nq, 148);
-  else census<128, 128, 5>(rows, k, nq, 148);
+  const bool concurrent = argc > 4 && atoi(argv[4]) != 0;     // all 148 CTAs resident together, as on the GPU
+  if (k <= 64) census<64, 64, 7>(rows, k, nq, 148, concurrent);
+  else census<128, 128, 5>(rows, k, nq, 148, concurrent);
   return 0;
 }

@@ -69,6 +69,10 @@ static std::vector<uint64_t> exact_keys(const std::vector<float>& s, int64_t row
   return all;
 }
 
+// 0: the scan's blocks run one after the other; otherwise: all resident together, advancing in a random interleaving drawn
+// from this seed (warp_emu::launch_concurrent) -- what one CTA publishes to the pool reaches the others mid-scan
+static uint64_t g_concurrent_seed = 0;
+
 // one pass = crag_search_scan + crag_search_finalize: scan shell on `grid` blocks, then the emulated merge kernel
 template <int KLIST, int CAP, int STAGES>
 static void run_pass(const std::vector<float>& scores, int64_t rows, int grid, int nq, int k, bool use_pool, uint32_t perm_mul, int perm_shift,
@@ -76,9 +80,11 @@ static void run_pass(const std::vector<float>& scores, int64_t rows, int grid, i
   std::vector<uint64_t> part_keys(size_t(grid) * kNQ * k, 0xDEADull), pool(size_t(grid) * kPoolSlots * kNQ, 0ull);
   std::vector<float> part_mm(size_t(grid) * kNQ * 2, -5.f);
   g_src = ScoreSource{scores.data(), rows, nullptr};
-  warp_emu::launch(grid, kSearchThreads, [&] {
+  auto scan = [&] {
     search_select_shell<KLIST, CAP, STAGES>(int(rows), nq, k, after, use_pool ? pool.data() : nullptr, perm_mul, perm_shift, part_keys.data(), part_mm.data(), NoIvfArgs{});
-  });
+  };
+  if (g_concurrent_seed) warp_emu::launch_concurrent(grid, kSearchThreads, scan, select_shell_smem_bytes<KLIST, CAP>(), g_concurrent_seed);
+  else warp_emu::launch(grid, kSearchThreads, scan, select_shell_smem_bytes<KLIST, CAP>());
   ids.assign(size_t(nq) * k, -5); sc.assign(size_t(nq) * k, -5.f); mm.assign(size_t(nq) * 2, -5.f); last.assign(nq, 1);
   warp_emu::launch(nq, 128, [&] {
     merge_topk_kernel<KLIST, CAP, false>(part_keys.data(), nullptr, nullptr, part_mm.data(), grid, kNQ, nq, k, 1000, 0, 0, 0, ids.data(), sc.data(), mm.data(), last.data());
@@ -105,8 +111,8 @@ static void test_topk(Data d, int grid, int tiles_per_cta, int ragged, int nq, i
     for (int64_t r = 0; r < rows; ++r) { mn = fminf(mn, scores[size_t(r) * kNQ + q]); mx = fmaxf(mx, scores[size_t(r) * kNQ + q]); }
     REQUIRE(mm[q * 2] == mn && mm[q * 2 + 1] == mx, "%s: (min, max) of query %d", name_of(d), q);
   }
-  printf("ok  select warps <%d, %d>: %s, %lld rows on %d CTAs (%d tiles each), nq = %d, k = %d, pool %s, permutation %s\n", KLIST, CAP, name_of(d),
-         (long long)rows, grid, tiles_per_cta, nq, k, use_pool ? "on" : "off", perm_mul ? "on" : "off");
+  printf("ok  select warps <%d, %d>: %s, %lld rows on %d CTAs (%d tiles each), nq = %d, k = %d, pool %s, permutation %s, CTAs %s\n", KLIST, CAP, name_of(d),
+         (long long)rows, grid, tiles_per_cta, nq, k, use_pool ? "on" : "off", perm_mul ? "on" : "off", g_concurrent_seed ? "interleaved" : "one after the other");
 }
 
 // rank continuation (crag_search_topk_after): pages of k ranks, each admitting only keys below the previous page's last
@@ -142,7 +148,7 @@ static void test_score_all(int grid, int tiles_per_cta, int nq) {
   g_src = ScoreSource{scores.data(), rows, nullptr};
   warp_emu::launch(grid, kSearchThreads, [&] {
     search_select_shell<16, 16, 9, false, true>(int(rows), nq, 1, nullptr, nullptr, 0u, 0, nullptr, part_mm.data(), ScoreArgs{out.data(), rows, nullptr, nullptr, 0});
-  });
+  }, select_shell_smem_bytes<16, 16>());
   for (int q = 0; q < nq; ++q) {
     float mn = INFINITY, mx = -INFINITY;
     for (int64_t r = 0; r < rows; ++r) {
@@ -190,7 +196,7 @@ static void test_ivf(int nlist, int nprobe, int grid, int nq, int k) {
   const IvfArgs args{work.data(), &n_work, mask.data(), coarse.data()};
   warp_emu::launch(grid, kSearchThreads, [&] {
     search_select_shell<KLIST, CAP, STAGES, true, false>(0, nq, k, nullptr, pool.data(), 0u, 0, part_keys.data(), part_mm.data(), args);
-  });
+  }, select_shell_smem_bytes<KLIST, CAP>());
   std::vector<int64_t> ids(size_t(nq) * k, -5);
   std::vector<float> sc(size_t(nq) * k, -5.f), mm(size_t(nq) * 2, -5.f);
   warp_emu::launch(nq, 128, [&] {
@@ -238,13 +244,19 @@ int main(int argc, char** argv) {
   test_topk<64, 64, 7>(Data::Random, 3, 5, 100, 7, 64, false, 0u, 0);          // no pool (short scans), nq < 32, k = KLIST
   test_topk<64, 64, 7>(Data::FewLevels, 5, 9, 1, 1, 1, true, 3u, 1);           // k = 1, one query
   // config 4's regime: k = 100 on the 128-key selector, batch-of-8 bisection floor (k <= 0.8 x CTAs) on 148 CTAs
-  for (Data d : {Data::Random, Data::AllEqual, Data::PlantedTail})
-    test_topk<128, 128, 5>(d, 148, 4, 77, 32, 100, true, 11u, 1);
+  test_topk<128, 128, 5>(Data::Random, 148, 4, 77, 32, 100, true, 11u, 1);
   test_topk<128, 128, 5>(Data::Ascending, 40, 10, 0, 32, 32, true, 7u, 2);     // 16 < k <= 0.8 x 40 CTAs
   // k > 0.8 x CTAs: all four keys per CTA pooled (pooled_kth_key), k = 128
-  for (Data d : {Data::Random, Data::FewLevels, Data::Ascending})
-    test_topk<128, 128, 5>(d, 8, 20, 5, 32, 128, true, 3u, 2);
+  test_topk<128, 128, 5>(Data::Ascending, 8, 20, 5, 32, 128, true, 3u, 2);
   test_topk<128, 128, 5>(Data::Random, 2, 1, 100, 32, 100, false, 0u, 0);       // fewer rows than k per CTA list: -1 padding
+  // the same regimes with all CTAs resident together, in two random interleavings each
+  for (uint64_t seed : {11ull, 12ull}) {
+    g_concurrent_seed = seed;
+    test_topk<64, 64, 7>(seed == 11 ? Data::Random : Data::FewLevels, 6, 30, 9, 32, 10, true, 37u, 3);
+    test_topk<128, 128, 5>(seed == 11 ? Data::AllEqual : Data::PlantedTail, 148, 4, 77, 32, 100, true, 11u, 1);
+    test_topk<128, 128, 5>(seed == 11 ? Data::FewLevels : Data::Random, 8, 20, 5, 32, 128, true, 3u, 2);
+  }
+  g_concurrent_seed = 0;
   test_continuation<128, 128, 5>(Data::Random, 4, 12, 5, 128, 4);
   test_continuation<128, 128, 5>(Data::FewLevels, 4, 6, 32, 128, 3);
   test_continuation<64, 64, 7>(Data::AllEqual, 3, 4, 3, 50, 5);

@@ -33,24 +33,31 @@ static inline void emu_tmem_ld(int tile, int quad, int lane, uint32_t (&r)[32]) 
 // the kernel's call is tmem_ld_32x32b_x32(<TMEM address>, r); `tile`, `quad`, `lane` are locals of the included text
 #define tmem_ld_32x32b_x32(addr, r) emu_tmem_ld(tile, quad, lane, r)
 
-// search_topk_kernel without its producer / MMA warps: same parameter names, same local names, the selector state in
-// block-shared arrays instead of carved out of dynamic shared memory
+// search_topk_kernel without its producer / MMA warps: same parameter names, same local names.  Launch with
+// select_shell_smem_bytes<KLIST, CAP>() of dynamic shared memory.
+template <int KLIST, int CAP>
+constexpr size_t select_shell_smem_bytes() {
+  return size_t(kNQ) * (KLIST + CAP) * 8 + 2 * kAccStages * 8 + kNQ * (8 + 4 + 4) + 4 * kNQ * 2 * 4 + kNQ * (8 + 4 + 8) + 4 * kNQ * 8 + 64;
+}
+
 template <int KLIST, int CAP, int STAGES, bool IVF = false, bool SCORES = false>
 static void search_select_shell(int n_rows, int nq, int k, const uint64_t* after_keys, uint64_t* pool, uint32_t perm_mul,
                                 int perm_shift, uint64_t* part_keys, float* part_minmax,
                                 const typename IvfParam<IVF, SCORES>::type ivf) {
   using L = SearchLayout<KLIST, CAP, STAGES>;
-  __shared__ uint64_t keys[kNQ * L::kKeysPerQuery];
-  __shared__ uint64_t bar_tfull[kAccStages];
-  __shared__ uint64_t bar_tempty[kAccStages];
-  __shared__ uint64_t thr_key[kNQ];
-  __shared__ float thr_f[kNQ];
-  __shared__ int cnt[kNQ];
-  __shared__ float red[4 * kNQ * 2];
-  __shared__ uint64_t bnd_key[kNQ];
-  __shared__ float bnd_f[kNQ];
-  __shared__ uint64_t floor_key[kNQ];
-  __shared__ uint64_t part_floor[4 * kNQ];
+  // the selector state, carved out of the block's dynamic shared memory as the kernel carves it out of smem_raw
+  uint8_t* smem = static_cast<uint8_t*>(warp_emu::dynamic_shared());
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* bar_tfull = keys + kNQ * L::kKeysPerQuery;          // [kAccStages]  (never waited on here)
+  uint64_t* bar_tempty = bar_tfull + kAccStages;                // [kAccStages]
+  uint64_t* thr_key = bar_tempty + kAccStages;                  // [kNQ]
+  float* thr_f = reinterpret_cast<float*>(thr_key + kNQ);       // [kNQ]
+  int* cnt = reinterpret_cast<int*>(thr_f + kNQ);               // [kNQ]
+  float* red = reinterpret_cast<float*>(cnt + kNQ);             // [4][kNQ][2]
+  uint64_t* bnd_key = reinterpret_cast<uint64_t*>(red + 4 * kNQ * 2);
+  float* bnd_f = reinterpret_cast<float*>(bnd_key + kNQ);
+  uint64_t* floor_key = reinterpret_cast<uint64_t*>(bnd_f + kNQ);
+  uint64_t* part_floor = floor_key + kNQ;                       // [4][kNQ]
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   int num_tiles;

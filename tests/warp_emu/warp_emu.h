@@ -16,6 +16,7 @@
 #include <string.h>
 #include <ucontext.h>
 
+#include <algorithm>
 #include <functional>
 #include <vector>
 
@@ -86,6 +87,8 @@ struct Block {
   bool named_or_acc[16] = {false}, named_or_result[16] = {false};
   std::vector<uint8_t> dyn_smem;  // the launch's dynamic shared memory (garbage-filled: CUDA does not zero it)
   uint64_t progress = 0;        // bumps whenever any barrier releases or a thread exits (deadlock detection)
+  int stuck_sweeps = 0;
+  uint64_t spinning_sweeps = 0;
   int cur = 0;
   unsigned block_idx = 0, grid_dim = 1;
   std::function<void()> body;
@@ -255,16 +258,13 @@ inline void trampoline() {
 #endif
 }
 
-// one thread block of n_threads CUDA threads (a multiple of 32), all running body() to completion
-inline void run_block(int n_threads, unsigned block_index, unsigned grid, const std::function<void()>& body,
-                      size_t dynamic_smem_bytes = 0) {
+// ---- a block's life: make_block(), sweep() until nothing is left alive, destroy_block()
+inline Block* make_block(int n_threads, unsigned block_index, unsigned grid, const std::function<void()>& body,
+                         size_t dynamic_smem_bytes, size_t stack_bytes) {
   if (n_threads % kLanes != 0) { fprintf(stderr, "warp_emu: block size must be a multiple of 32\n"); abort(); }
   Block* b = new Block;
-  Block* outer = current();
-  current() = b;
   b->body = body;
   b->dyn_smem.assign(dynamic_smem_bytes + 16, 0xCD);
-  nap_armed() = true;
   b->n_threads = b->live = n_threads;
   b->block_idx = block_index;
   b->grid_dim = grid;
@@ -273,11 +273,11 @@ inline void run_block(int n_threads, unsigned block_index, unsigned grid, const 
   for (auto& w : b->warps) w.live = kLanes;
   for (int t = 0; t < n_threads; ++t) {
     Fiber& f = b->fibers[t];
-    f.stack = static_cast<char*>(malloc(kStackBytes));
+    f.stack = static_cast<char*>(malloc(stack_bytes));
 #ifdef WARP_EMU_FAST_SWITCH
     // initial frame: six callee-saved registers, then the entry point as the address `ret` jumps to, then a dummy
     // return address so the entry function sees the stack alignment of an ordinary call
-    uintptr_t top = (reinterpret_cast<uintptr_t>(f.stack) + kStackBytes) & ~uintptr_t(15);
+    uintptr_t top = (reinterpret_cast<uintptr_t>(f.stack) + stack_bytes) & ~uintptr_t(15);
     void** frame = reinterpret_cast<void**>(top) - 8;
     for (int i = 0; i < 6; ++i) frame[i] = nullptr;
     frame[6] = reinterpret_cast<void*>(&trampoline);
@@ -286,48 +286,86 @@ inline void run_block(int n_threads, unsigned block_index, unsigned grid, const 
 #else
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = f.stack;
-    f.ctx.uc_stack.ss_size = kStackBytes;
+    f.ctx.uc_stack.ss_size = stack_bytes;
     f.ctx.uc_link = &b->main;
     makecontext(&f.ctx, reinterpret_cast<void (*)()>(trampoline), 0);
 #endif
   }
-  int stuck_sweeps = 0;
-  uint64_t spinning_sweeps = 0;
-  while (b->live > 0) {
-    const uint64_t before = b->progress;
-    const uint64_t spins_before = spin_count();
-    const int arrived_before = b->bar_arrived;
-    int warp_arrived_before = 0;
-    for (auto& w : b->warps) warp_arrived_before += w.arrived;
-    for (int i = 0; i < 16; ++i) warp_arrived_before += b->named_arrived[i];
-    for (int t = 0; t < n_threads; ++t) {
-      if (b->fibers[t].done) continue;
-      b->cur = t;
-#ifdef WARP_EMU_FAST_SWITCH
-      warp_emu_switch(&b->main_sp, b->fibers[t].sp);
-#else
-      swapcontext(&b->main, &b->fibers[t].ctx);
-#endif
-    }
-    int warp_arrived_after = 0;
-    for (auto& w : b->warps) warp_arrived_after += w.arrived;
-    for (int i = 0; i < 16; ++i) warp_arrived_after += b->named_arrived[i];
-    if (b->progress == before && b->bar_arrived == arrived_before && warp_arrived_after == warp_arrived_before && b->live > 0) {
-      // nothing moved in a whole sweep.  Threads sleeping in a spin-wait on memory another OS thread will write (the
-      // exchange kernel's flag wait) are legitimate and get a long leash; anything else is a lost collective.
-      const bool spinning = spin_count() != spins_before;
-      if (spinning ? ++spinning_sweeps > (uint64_t(1) << 24) : ++stuck_sweeps > 4) {
-        fprintf(stderr, "warp_emu: deadlock in block %u -- %d live threads, %d at __syncthreads, %d at warp collectives\n",
-                block_index, b->live, b->bar_arrived, warp_arrived_after);
-        abort();
-      }
-    } else {
-      stuck_sweeps = 0;
-    }
-  }
+  return b;
+}
+
+inline void destroy_block(Block* b) {
   for (auto& f : b->fibers) free(f.stack);
   delete b;
+}
+
+// every live thread of the block runs up to its next synchronisation point; false once the block has finished
+inline bool sweep(Block* b) {
+  Block* outer = current();
+  current() = b;
+  const uint64_t before = b->progress;
+  const uint64_t spins_before = spin_count();
+  const int arrived_before = b->bar_arrived;
+  int warp_arrived_before = 0;
+  for (auto& w : b->warps) warp_arrived_before += w.arrived;
+  for (int i = 0; i < 16; ++i) warp_arrived_before += b->named_arrived[i];
+  for (int t = 0; t < b->n_threads; ++t) {
+    if (b->fibers[t].done) continue;
+    b->cur = t;
+#ifdef WARP_EMU_FAST_SWITCH
+    warp_emu_switch(&b->main_sp, b->fibers[t].sp);
+#else
+    swapcontext(&b->main, &b->fibers[t].ctx);
+#endif
+  }
+  int warp_arrived_after = 0;
+  for (auto& w : b->warps) warp_arrived_after += w.arrived;
+  for (int i = 0; i < 16; ++i) warp_arrived_after += b->named_arrived[i];
+  if (b->progress == before && b->bar_arrived == arrived_before && warp_arrived_after == warp_arrived_before && b->live > 0) {
+    // nothing moved in a whole sweep.  Threads sleeping in a spin-wait on memory another OS thread will write (the
+    // exchange kernel's flag wait) are legitimate and get a long leash; anything else is a lost collective.
+    const bool spinning = spin_count() != spins_before;
+    if (spinning ? ++b->spinning_sweeps > (uint64_t(1) << 24) : ++b->stuck_sweeps > 4) {
+      fprintf(stderr, "warp_emu: deadlock in block %u -- %d live threads, %d at __syncthreads, %d at warp collectives\n",
+              b->block_idx, b->live, b->bar_arrived, warp_arrived_after);
+      abort();
+    }
+  } else {
+    b->stuck_sweeps = 0;
+  }
   current() = outer;
+  return b->live > 0;
+}
+
+inline void run_block(int n_threads, unsigned block_index, unsigned grid, const std::function<void()>& body,
+                      size_t dynamic_smem_bytes = 0) {
+  Block* b = make_block(n_threads, block_index, grid, body, dynamic_smem_bytes, kStackBytes);
+  nap_armed() = true;
+  while (sweep(b)) {}
+  destroy_block(b);
+}
+
+// kernel<<<grid, block>>> with all blocks RESIDENT TOGETHER (a persistent kernel: one block per SM): the blocks advance
+// in turns, in an order drawn afresh from `seed` every round and by a random number of steps each, so that what one
+// block publishes in global memory reaches the others at arbitrary points of their own progress.  Block-local storage
+// must come from dynamic shared memory (each block has its own); `static` storage would be shared by all of them.
+inline void launch_concurrent(unsigned grid, int block, const std::function<void()>& kernel_call, size_t dynamic_smem_bytes,
+                              uint64_t seed, size_t stack_bytes = 96 << 10) {
+  std::vector<Block*> blocks(grid);
+  for (unsigned i = 0; i < grid; ++i) blocks[i] = make_block(block, i, grid, kernel_call, dynamic_smem_bytes, stack_bytes);
+  uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto next = [&]() { x ^= x >> 12; x ^= x << 25; x ^= x >> 27; return x * 0x2545F4914F6CDD1Dull; };
+  std::vector<unsigned> alive(grid);
+  for (unsigned i = 0; i < grid; ++i) alive[i] = i;
+  while (!alive.empty()) {
+    for (size_t i = alive.size(); i > 1; --i) std::swap(alive[i - 1], alive[next() % i]);
+    for (size_t i = 0; i < alive.size();) {
+      bool more = true;
+      for (int steps = 1 + int(next() % 3); steps > 0 && more; --steps) more = sweep(blocks[alive[i]]);
+      if (!more) { alive[i] = alive.back(); alive.pop_back(); } else { ++i; }
+    }
+  }
+  for (Block* b : blocks) destroy_block(b);
 }
 
 // kernel<<<grid, block>>>: blocks run one after the other
