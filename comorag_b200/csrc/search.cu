@@ -180,16 +180,6 @@ struct SearchPlan {
   size_t pool_bytes;    // pooled-floor table of one 32-query pass (0 when the grid exceeds kPoolMaxCtas)
 };
 
-// multiplier of the group permutation g -> (g * P) mod n_groups: near n_groups / golden ratio, coprime to n_groups
-// (0 = identity / permutation off)
-uint32_t perm_multiplier(int64_t num_tiles) {
-  if (num_tiles < 4) return 0u;
-  auto gcd = [](uint64_t a, uint64_t b) { while (b) { const uint64_t t = a % b; a = b; b = t; } return a; };
-  uint64_t p = (uint64_t(double(num_tiles) * 0.6180339887498949) | 1ull);
-  while (gcd(p, uint64_t(num_tiles)) != 1) p += 2;
-  return uint32_t(p % uint64_t(num_tiles));
-}
-
 SearchPlan plan_search(int k) {
   SearchPlan p;
   p.grid = sm_count();

@@ -13,15 +13,6 @@
 
 using namespace crag;
 
-// multiplier of the tile-group permutation, as search.cu's perm_multiplier() picks it
-static uint32_t perm_multiplier(int64_t groups) {
-  if (groups < 4) return 0u;
-  auto gcd = [](uint64_t a, uint64_t b) { while (b) { const uint64_t t = a % b; a = b; b = t; } return a; };
-  uint64_t p = (uint64_t(double(groups) * 0.6180339887498949) | 1ull);
-  while (gcd(p, uint64_t(groups)) != 1) p += 2;
-  return uint32_t(p % uint64_t(groups));
-}
-
 template <int KLIST, int CAP, int STAGES>
 static void census(int64_t rows, int k, int nq, int grid, bool concurrent) {
   std::mt19937_64 rng(5);

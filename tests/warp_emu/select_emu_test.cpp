@@ -91,9 +91,18 @@ static void run_pass(const std::vector<float>& scores, int64_t rows, int grid, i
   });
 }
 
+constexpr uint32_t kAutoPerm = 0xFFFFFFFFu;     // "ask perm_multiplier()", as the library's host code does
+
 template <int KLIST, int CAP, int STAGES>
 static void test_topk(Data d, int grid, int tiles_per_cta, int ragged, int nq, int k, bool use_pool, uint32_t perm_mul, int perm_shift) {
   const int64_t rows = int64_t(grid) * tiles_per_cta * kTileRows - ragged;
+  const int64_t n_tiles = (rows + kTileRows - 1) / kTileRows;
+  if (perm_mul == kAutoPerm) perm_mul = perm_multiplier(n_tiles >> perm_shift);
+  else if (perm_mul) {      // a hand-picked multiplier must be a bijection of the tile groups
+    int64_t a = perm_mul, b = n_tiles >> perm_shift;
+    while (b) { const int64_t t = a % b; a = b; b = t; }
+    REQUIRE(a == 1, "test bug: multiplier %u is not coprime to %lld tile groups", perm_mul, (long long)(n_tiles >> perm_shift));
+  }
   std::vector<float> scores = make_scores(rows, d);
   std::vector<int64_t> ids;
   std::vector<float> sc, mm;
@@ -233,6 +242,24 @@ int main(int argc, char** argv) {
     test_topk<64, 64, 7>(Data::FewLevels, 4, 8, 33, 32, 10, true, 37u, 3);
     test_continuation<128, 128, 5>(Data::FewLevels, 4, 6, 32, 128, 3);
     test_continuation<64, 64, 7>(Data::AllEqual, 3, 4, 3, 50, 5);
+    printf("ALL OK\n");
+    return 0;
+  }
+  if (argc > 2 && std::string(argv[1]) == "fuzz") {     // fuzz FIRST_SEED COUNT: random regimes, CTAs interleaved by seed
+    const uint64_t first = strtoull(argv[2], nullptr, 10), count = argc > 3 ? strtoull(argv[3], nullptr, 10) : 10;
+    for (uint64_t seed = first; seed < first + count; ++seed) {
+      rng.seed(seed * 7919);
+      g_concurrent_seed = getenv("FUZZ_SEQUENTIAL") ? 0 : seed;
+      const Data d = Data(rng() % 5);
+      const int regime = int(rng() % 4);
+      const int ragged = int(rng() % 128), nq = (rng() % 3 == 0) ? 1 + int(rng() % 32) : 32;
+      // kAutoPerm: the multiplier search.cu's perm_multiplier() picks for the drawn shape (it must be coprime to the
+      // number of tile groups -- an arbitrary constant would visit some tiles twice and others never)
+      if (regime == 0) test_topk<64, 64, 7>(d, 2 + int(rng() % 10), 3 + int(rng() % 20), ragged, nq, 1 + int(rng() % 16), true, kAutoPerm, int(rng() % 4));
+      else if (regime == 1) test_topk<64, 64, 7>(d, 20 + int(rng() % 60), 3 + int(rng() % 6), ragged, nq, 17 + int(rng() % 48), true, kAutoPerm, int(rng() % 3));
+      else if (regime == 2) test_topk<128, 128, 5>(d, 130 + int(rng() % 30), 3 + int(rng() % 3), ragged, nq, 65 + int(rng() % 40), true, kAutoPerm, 1);
+      else test_topk<128, 128, 5>(d, 4 + int(rng() % 12), 4 + int(rng() % 12), ragged, nq, 100 + int(rng() % 29), true, kAutoPerm, int(rng() % 3));
+    }
     printf("ALL OK\n");
     return 0;
   }
