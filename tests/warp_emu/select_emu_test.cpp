@@ -134,7 +134,8 @@ static void test_continuation(Data d, int grid, int tiles_per_cta, int nq, int k
     std::vector<int64_t> ids;
     std::vector<float> sc, mm;
     std::vector<uint64_t> last;
-    run_pass<KLIST, CAP, STAGES>(scores, rows, grid, nq, k, true, 5u, 1, page ? after.data() : nullptr, ids, sc, mm, last);
+    run_pass<KLIST, CAP, STAGES>(scores, rows, grid, nq, k, true, perm_multiplier(((rows + kTileRows - 1) / kTileRows) >> 1), 1,
+                                 page ? after.data() : nullptr, ids, sc, mm, last);
     for (int q = 0; q < nq; ++q) {
       std::vector<uint64_t> want = exact_keys(scores, rows, q);
       for (int j = 0; j < k; ++j) {
@@ -251,14 +252,21 @@ int main(int argc, char** argv) {
       rng.seed(seed * 7919);
       g_concurrent_seed = getenv("FUZZ_SEQUENTIAL") ? 0 : seed;
       const Data d = Data(rng() % 5);
-      const int regime = int(rng() % 4);
+      const int regime = int(rng() % 6);
       const int ragged = int(rng() % 128), nq = (rng() % 3 == 0) ? 1 + int(rng() % 32) : 32;
       // kAutoPerm: the multiplier search.cu's perm_multiplier() picks for the drawn shape (it must be coprime to the
       // number of tile groups -- an arbitrary constant would visit some tiles twice and others never)
       if (regime == 0) test_topk<64, 64, 7>(d, 2 + int(rng() % 10), 3 + int(rng() % 20), ragged, nq, 1 + int(rng() % 16), true, kAutoPerm, int(rng() % 4));
       else if (regime == 1) test_topk<64, 64, 7>(d, 20 + int(rng() % 60), 3 + int(rng() % 6), ragged, nq, 17 + int(rng() % 48), true, kAutoPerm, int(rng() % 3));
       else if (regime == 2) test_topk<128, 128, 5>(d, 130 + int(rng() % 30), 3 + int(rng() % 3), ragged, nq, 65 + int(rng() % 40), true, kAutoPerm, 1);
-      else test_topk<128, 128, 5>(d, 4 + int(rng() % 12), 4 + int(rng() % 12), ragged, nq, 100 + int(rng() % 29), true, kAutoPerm, int(rng() % 3));
+      else if (regime == 3) test_topk<128, 128, 5>(d, 4 + int(rng() % 12), 4 + int(rng() % 12), ragged, nq, 100 + int(rng() % 29), true, kAutoPerm, int(rng() % 3));
+      else if (regime == 4) {
+        if (rng() % 2) test_continuation<128, 128, 5>(d, 2 + int(rng() % 6), 2 + int(rng() % 8), nq, 65 + int(rng() % 64), 2 + int(rng() % 3));
+        else test_continuation<64, 64, 7>(d, 2 + int(rng() % 6), 2 + int(rng() % 8), nq, 1 + int(rng() % 64), 2 + int(rng() % 4));
+      } else {
+        if (rng() % 2) test_ivf<128, 128, 5>(8 + int(rng() % 200), 1 + int(rng() % 8), 1 + int(rng() % 9), nq, 65 + int(rng() % 64));
+        else test_ivf<64, 64, 7>(8 + int(rng() % 200), 1 + int(rng() % 8), 1 + int(rng() % 9), nq, 1 + int(rng() % 64));
+      }
     }
     printf("ALL OK\n");
     return 0;
